@@ -1,0 +1,415 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  out = epilogue(A[M,K] @ W[N,K]^T).
+//
+//   warp 0      : TMA producer  (A 128x64 and W BNx64 boxes, SWIZZLE_128B, STAGES-deep mbarrier ring)
+//   warp 1      : tcgen05.mma issuer (one elected thread; UMMA 128 x BN x 16, fp32 accumulators in TMEM,
+//                 two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//
+// Both operands are K-major (activations row-major, nn.Linear weights [out,in]) so no transposes are needed.
+// The fused epilogues implement the reference's per-layer elementwise work (bias, GELU-tanh, adaLN-gated
+// residual, control add, QKV split + per-head QK-LayerNorm, patch-embed position add, unpatchify); see
+// include/landiff_b200.h for the reference lines each one replaces.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace ld {
+
+using bf16 = __nv_bfloat16;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int BM = 128;
+  static constexpr int BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 192) ? 5 : (BN >= 128 ? 6 : 8);
+  static constexpr uint32_t TMEM_COLS = (BN <= 64) ? 128 : (BN <= 128 ? 256 : 512);
+  static constexpr int ACC_STRIDE = TMEM_COLS / 2;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+constexpr int kGemmThreads = 192;
+
+struct RowCtx {
+  int row;        // A row
+  bool valid;
+  int b;          // sample
+  int t;          // token within the local shard
+  bool is_text;
+  int64_t out_row;
+};
+
+__device__ __forceinline__ void load8_bf16(const bf16* p, float* f) {
+  uint4 v = *reinterpret_cast<const uint4*>(p);
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ void store8_bf16(bf16* p, const float* f) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+
+// ---- epilogues on a 32-column chunk held by one thread (one output row) -------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue32(const ld_gemm_args& p, const RowCtx& rc, int col, const uint32_t* r) {
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(r[i]);
+
+  if constexpr (EPI != LD_EPI_NONE) {
+    if (p.bias != nullptr) {
+      const bf16* bias = reinterpret_cast<const bf16*>(p.bias) + col;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float bv[8];
+        load8_bf16(bias + g * 8, bv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[g * 8 + i] += bv[i];
+      }
+    }
+  }
+  if (!rc.valid) return;
+
+  if constexpr (EPI == LD_EPI_NONE || EPI == LD_EPI_BIAS || EPI == LD_EPI_BIAS_GELU) {
+    if constexpr (EPI == LD_EPI_BIAS_GELU) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = gelu_tanh(acc[i]);
+    }
+    bf16* o = reinterpret_cast<bf16*>(p.out) + rc.out_row * p.ld_out + col;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) store8_bf16(o + g * 8, acc + g * 8);
+  } else if constexpr (EPI == LD_EPI_GATED_RESID) {
+    const float* gate = (rc.is_text ? p.gate_txt : p.gate_img) + (int64_t)rc.b * p.mod_batch_stride + col;
+    const bf16* res = reinterpret_cast<const bf16*>(p.resid) + rc.out_row * p.ld_out + col;
+    const bf16* add2 = p.add2 ? reinterpret_cast<const bf16*>(p.add2) + rc.out_row * p.ld_out + col : nullptr;
+    bf16* o = reinterpret_cast<bf16*>(p.out) + rc.out_row * p.ld_out + col;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float rv[8];
+      load8_bf16(res + g * 8, rv);
+      const float4 g0 = *reinterpret_cast<const float4*>(gate + g * 8);
+      const float4 g1 = *reinterpret_cast<const float4*>(gate + g * 8 + 4);
+      const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      float ov[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ov[i] = fmaf(gv[i], acc[g * 8 + i], rv[i]);
+      if (add2 != nullptr) {
+        float av[8];
+        load8_bf16(add2 + g * 8, av);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ov[i] += av[i];
+      }
+      store8_bf16(o + g * 8, ov);
+    }
+  } else if constexpr (EPI == LD_EPI_BIAS_POS) {
+    const bf16* pos = reinterpret_cast<const bf16*>(p.pos) + (int64_t)(p.tok_offset + rc.t) * p.N + col;
+    bf16* o = reinterpret_cast<bf16*>(p.out) + rc.out_row * p.ld_out + col;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float pv[8];
+      load8_bf16(pos + g * 8, pv);
+      float ov[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ov[i] = acc[g * 8 + i] + pv[i];
+      store8_bf16(o + g * 8, ov);
+    }
+  } else if constexpr (EPI == LD_EPI_UNPATCHIFY) {
+    // col = c*4 + pp*2 + qq  ->  out[b, t, c, 2h+pp, 2w+qq]      (dit_video_concat.py:392-410)
+    const int g = p.tok_offset + rc.t - p.text_len;
+    const int hw = p.Hp * p.Wp;
+    const int tt = g / hw, rem = g - tt * hw;
+    const int h = rem / p.Wp, w = rem - h * p.Wp;
+    const int H = 2 * p.Hp, W = 2 * p.Wp;
+    bf16* o = reinterpret_cast<bf16*>(p.out);
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const int cc = col + i;
+      const int c = cc >> 2, pp = (cc >> 1) & 1;
+      const int64_t idx = (((int64_t)(rc.b * p.T + tt) * p.C + c) * H + (2 * h + pp)) * W + 2 * w;
+      *reinterpret_cast<uint32_t*>(o + idx) = pack_bf16x2(acc[i], acc[i + 1]);
+    }
+  }
+}
+
+// QKV epilogue on one 64-column head slice: split, per-head LayerNorm for Q/K, head-major store.
+__device__ __forceinline__ void epilogue_qkv64(const ld_gemm_args& p, const RowCtx& rc, int col, const uint32_t* r0,
+                                               const uint32_t* r1) {
+  float acc[64];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    acc[i] = __uint_as_float(r0[i]);
+    acc[32 + i] = __uint_as_float(r1[i]);
+  }
+  const bf16* bias = reinterpret_cast<const bf16*>(p.bias) + col;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float bv[8];
+    load8_bf16(bias + g * 8, bv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[g * 8 + i] += bv[i];
+  }
+  if (!rc.valid) return;
+  const int hd_all = p.heads * 64;
+  const int which = col / hd_all;  // 0 q, 1 k, 2 v
+  const int head = (col - which * hd_all) >> 6;
+  if (which < 2) {
+    // the reference rounds the QKV projection to bf16 before the LayerNorm; keep that rounding point
+    float mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      acc[i] = __bfloat162float(__float2bfloat16_rn(acc[i]));
+      mean += acc[i];
+    }
+    mean *= (1.0f / 64.0f);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) {
+      const float d = acc[i] - mean;
+      var = fmaf(d, d, var);
+    }
+    const float rstd = rsqrtf(var * (1.0f / 64.0f) + p.ln_eps);
+    const bf16* w = reinterpret_cast<const bf16*>(which == 0 ? p.q_ln_w : p.k_ln_w);
+    const bf16* b = reinterpret_cast<const bf16*>(which == 0 ? p.q_ln_b : p.k_ln_b);
+    const float post = (which == 0) ? p.q_scale : 1.0f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float wv[8], bv[8];
+      load8_bf16(w + g * 8, wv);
+      load8_bf16(b + g * 8, bv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = fmaf((acc[g * 8 + i] - mean) * rstd, wv[i], bv[i]);
+        if (which == 0) y = __bfloat162float(__float2bfloat16_rn(y)) * post;  // bf16 LN output, then scale
+        acc[g * 8 + i] = y;
+      }
+    }
+  }
+  bf16* base = reinterpret_cast<bf16*>(which == 0 ? p.q : (which == 1 ? p.k : p.v));
+  bf16* o = base + (((int64_t)rc.b * p.heads + head) * p.qkv_rows + p.qkv_row_offset + rc.t) * 64;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) store8_bf16(o + g * 8, acc + g * 8);
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const ld_gemm_args p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (p.M + Cfg::BM - 1) / Cfg::BM;
+  const int num_n = p.N / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = p.K / Cfg::BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * Cfg::BM;
+        const int n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          tma_load_2d(sA + s * Cfg::A_BYTES, &tmap_a, &full_bar[s], kb * Cfg::BK, m0);
+          tma_load_2d(sB + s * Cfg::B_BYTES, &tmap_b, &full_bar[s], kb * Cfg::BK, n0);
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(Cfg::BM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t adesc = make_sdesc_sw128(smem_u32(sA + s * Cfg::A_BYTES));
+          const uint64_t bdesc = make_sdesc_sw128(smem_u32(sB + s * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < Cfg::BK / 16; ++k) {
+            // +32 bytes (encoded >>4 = 2) per 16-element K step inside the 128-byte swizzle span
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row_in_tile = quad * 32 + lane;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * Cfg::BM;
+      const int n0 = (tile % num_n) * BN;
+      RowCtx rc;
+      rc.row = m0 + row_in_tile;
+      rc.valid = rc.row < p.M;
+      const int rr = rc.valid ? rc.row : 0;
+      rc.b = rr / p.rows_per_batch;
+      rc.t = rr - rc.b * p.rows_per_batch;
+      rc.is_text = (p.tok_offset + rc.t) < p.text_len;
+      rc.out_row = (int64_t)rc.b * p.out_rows_per_batch + p.out_row_offset + rc.t;
+
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + as * Cfg::ACC_STRIDE;
+      if constexpr (EPI == LD_EPI_QKV) {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+          uint32_t r0[32], r1[32];
+          LD_TMEM_LD32(taddr + c, r0);
+          LD_TMEM_LD32(taddr + c + 32, r1);
+          tmem_ld_wait();
+          epilogue_qkv64(p, rc, n0 + c, r0, r1);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          LD_TMEM_LD32(taddr + c, r);
+          tmem_ld_wait();
+          epilogue32<EPI>(p, rc, n0 + c, r);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const ld_gemm_args& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+    const uint64_t str[1] = {(uint64_t)a.K * 2};
+    const uint32_t box[2] = {64, 128};
+    int rc = make_tmap_bf16(&ta, a.A, 2, dims, str, box);
+    if (rc != LD_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+    const uint64_t str[1] = {(uint64_t)a.K * 2};
+    const uint32_t box[2] = {64, (uint32_t)BN};
+    int rc = make_tmap_bf16(&tb, a.W, 2, dims, str, box);
+    if (rc != LD_OK) return rc;
+  }
+  auto kern = gemm_kernel<BN, EPI>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_tiles = ((a.M + 127) / 128) * (a.N / BN);
+  const int grid = num_tiles < sm_count() ? num_tiles : sm_count();
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, a);
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}
+
+template <int EPI>
+static int dispatch_bn(const ld_gemm_args& a, cudaStream_t stream) {
+  if (a.N % 192 == 0) return launch_gemm<192, EPI>(a, stream);
+  if (a.N % 128 == 0) return launch_gemm<128, EPI>(a, stream);
+  return launch_gemm<64, EPI>(a, stream);
+}
+
+}  // namespace ld
+
+extern "C" int ld_gemm_bf16(const ld_gemm_args* args, void* stream) {
+  using namespace ld;
+  int rc = check_device();
+  if (rc != LD_OK) return rc;
+  LD_CHECK_ARG(args != nullptr, "ld_gemm_bf16: null args");
+  const ld_gemm_args& a = *args;
+  LD_CHECK_ARG(a.M > 0 && a.N > 0 && a.K > 0, "ld_gemm_bf16: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
+  LD_CHECK_ARG(a.K % 64 == 0, "ld_gemm_bf16: K=%d must be a multiple of 64", a.K);
+  LD_CHECK_ARG(a.N % 64 == 0, "ld_gemm_bf16: N=%d must be a multiple of 64", a.N);
+  LD_CHECK_ARG(a.A && a.W, "ld_gemm_bf16: null operand");
+  LD_CHECK_ARG(a.rows_per_batch > 0 && a.M % a.rows_per_batch == 0,
+               "ld_gemm_bf16: M=%d not a multiple of rows_per_batch=%d", a.M, a.rows_per_batch);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (a.epilogue != LD_EPI_QKV) {
+    LD_CHECK_ARG(a.out != nullptr, "ld_gemm_bf16: null out");
+    LD_CHECK_ARG(a.epilogue == LD_EPI_UNPATCHIFY || (a.ld_out >= a.N && a.ld_out % 8 == 0),
+                 "ld_gemm_bf16: ld_out=%lld must be >= N and a multiple of 8", (long long)a.ld_out);
+  }
+  switch (a.epilogue) {
+    case LD_EPI_NONE: return dispatch_bn<LD_EPI_NONE>(a, st);
+    case LD_EPI_BIAS: return dispatch_bn<LD_EPI_BIAS>(a, st);
+    case LD_EPI_BIAS_GELU: return dispatch_bn<LD_EPI_BIAS_GELU>(a, st);
+    case LD_EPI_GATED_RESID:
+      LD_CHECK_ARG(a.resid && a.gate_img && a.gate_txt, "ld_gemm_bf16: GATED_RESID needs resid and gates");
+      return dispatch_bn<LD_EPI_GATED_RESID>(a, st);
+    case LD_EPI_QKV:
+      LD_CHECK_ARG(a.q && a.k && a.v && a.bias && a.q_ln_w && a.q_ln_b && a.k_ln_w && a.k_ln_b,
+                   "ld_gemm_bf16: QKV needs q/k/v, bias and LayerNorm parameters");
+      LD_CHECK_ARG(a.heads > 0 && a.N == 3 * a.heads * 64, "ld_gemm_bf16: QKV needs N == 3*heads*64");
+      LD_CHECK_ARG(a.qkv_rows >= a.qkv_row_offset + a.rows_per_batch, "ld_gemm_bf16: qkv_rows too small");
+      return dispatch_bn<LD_EPI_QKV>(a, st);
+    case LD_EPI_BIAS_POS:
+      LD_CHECK_ARG(a.pos != nullptr, "ld_gemm_bf16: BIAS_POS needs pos");
+      return dispatch_bn<LD_EPI_BIAS_POS>(a, st);
+    case LD_EPI_UNPATCHIFY:
+      LD_CHECK_ARG(a.N == 64 && a.C == 16 && a.T > 0 && a.Hp > 0 && a.Wp > 0,
+                   "ld_gemm_bf16: UNPATCHIFY needs N=64, C=16 and the patch grid");
+      return dispatch_bn<LD_EPI_UNPATCHIFY>(a, st);
+    default:
+      set_error("ld_gemm_bf16: unknown epilogue %d", a.epilogue);
+      return LD_ERR_ARG;
+  }
+}

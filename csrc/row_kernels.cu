@@ -1,0 +1,407 @@
+// Memory-bound fused kernels of the DiT hot path: adaLN-modulated LayerNorm (warp per row, 16-byte vector
+// loads, row kept in registers), the double-LayerNorm final-layer front half, patchify (im2col of the 2x2/s2
+// conv, fused with the semantic-feature add), tiny-batch GEMV for time_embed / adaLN projections, the
+// sinusoidal timestep embedding and the fused denoiser-scale + CFG + DPM++(2M) SDE update.
+// Reference lines: see include/landiff_b200.h.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace ld {
+
+using bf16 = __nv_bfloat16;
+constexpr int kMaxVec = 8;  // per-lane 16-byte vectors: D <= 32*8*8 = 2048
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+  v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+  return v;
+}
+
+// LayerNorm statistics of a row held as vals[kMaxVec][8] (lanes own vectors lane, lane+32, ...).
+__device__ __forceinline__ void row_stats(const float (*vals)[8], int nvec, int lane, int D, float eps, float& mean,
+                                          float& rstd) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i)
+    if (lane + 32 * i < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += vals[i][j];
+    }
+  mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i)
+    if (lane + 32 * i < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = vals[i][j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+}
+
+// out = LN(x) * (1 + scale[seg]) + shift[seg]
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict__ x, bf16* __restrict__ out,
+                                                          const bf16* __restrict__ w, const bf16* __restrict__ b,
+                                                          float eps, const float* __restrict__ shift_img,
+                                                          const float* __restrict__ scale_img,
+                                                          const float* __restrict__ shift_txt,
+                                                          const float* __restrict__ scale_txt, int64_t mod_stride,
+                                                          int rows, int rows_per_batch, int tok_offset, int text_len,
+                                                          int D) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = D >> 3;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+    const int bidx = row / rows_per_batch;
+    const int t = row - bidx * rows_per_batch;
+    const bool is_text = (tok_offset + t) < text_len;
+    const float* shift = (is_text ? shift_txt : shift_img) + (int64_t)bidx * mod_stride;
+    const float* scale = (is_text ? scale_txt : scale_img) + (int64_t)bidx * mod_stride;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * D);
+    float vals[kMaxVec][8];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (lane + 32 * i < nvec) unpack8(xr[lane + 32 * i], vals[i]);
+    float mean, rstd;
+    row_stats(vals, nvec, lane, D, eps, mean, rstd);
+    uint4* orow = reinterpret_cast<uint4*>(out + (int64_t)row * D);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float wv[8], bv[8], o[8];
+        unpack8(reinterpret_cast<const uint4*>(w)[v], wv);
+        unpack8(reinterpret_cast<const uint4*>(b)[v], bv);
+        const float4 sc0 = reinterpret_cast<const float4*>(scale)[2 * v], sc1 = reinterpret_cast<const float4*>(scale)[2 * v + 1];
+        const float4 sh0 = reinterpret_cast<const float4*>(shift)[2 * v], sh1 = reinterpret_cast<const float4*>(shift)[2 * v + 1];
+        const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+        const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float y = fmaf((vals[i][j] - mean) * rstd, wv[j], bv[j]);
+          o[j] = fmaf(y, 1.0f + sc[j], sh[j]);
+        }
+        orow[v] = pack8(o);
+      }
+    }
+  }
+}
+
+// y = LN2(LN1(x_img)) * (1 + scale) + shift ; only image rows are produced (compacted)
+__global__ void __launch_bounds__(256) final_norm_kernel(const bf16* __restrict__ x, bf16* __restrict__ out,
+                                                         const bf16* __restrict__ w1, const bf16* __restrict__ b1,
+                                                         float eps1, const bf16* __restrict__ w2,
+                                                         const bf16* __restrict__ b2, float eps2,
+                                                         const float* __restrict__ shift, const float* __restrict__ scale,
+                                                         int64_t mod_stride, int batch, int rows_per_batch, int first_img,
+                                                         int D) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = D >> 3;
+  const int n_img = rows_per_batch - first_img;
+  const int rows = batch * n_img;
+  for (int orow_i = blockIdx.x * wpb + (threadIdx.x >> 5); orow_i < rows; orow_i += gridDim.x * wpb) {
+    const int bidx = orow_i / n_img;
+    const int g = orow_i - bidx * n_img;
+    const int64_t in_row = (int64_t)bidx * rows_per_batch + first_img + g;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + in_row * D);
+    float vals[kMaxVec][8];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i)
+      if (lane + 32 * i < nvec) unpack8(xr[lane + 32 * i], vals[i]);
+    float mean, rstd;
+    row_stats(vals, nvec, lane, D, eps1, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float wv[8], bv[8];
+        unpack8(reinterpret_cast<const uint4*>(w1)[v], wv);
+        unpack8(reinterpret_cast<const uint4*>(b1)[v], bv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // SAT final_layernorm output is a bf16 tensor in the reference
+          vals[i][j] = __bfloat162float(__float2bfloat16_rn(fmaf((vals[i][j] - mean) * rstd, wv[j], bv[j])));
+      }
+    }
+    row_stats(vals, nvec, lane, D, eps2, mean, rstd);
+    const float* sh_p = shift + (int64_t)bidx * mod_stride;
+    const float* sc_p = scale + (int64_t)bidx * mod_stride;
+    uint4* orow = reinterpret_cast<uint4*>(out + (int64_t)orow_i * D);
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float wv[8], bv[8], o[8];
+        unpack8(reinterpret_cast<const uint4*>(w2)[v], wv);
+        unpack8(reinterpret_cast<const uint4*>(b2)[v], bv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float y = fmaf((vals[i][j] - mean) * rstd, wv[j], bv[j]);
+          o[j] = fmaf(y, 1.0f + sc_p[v * 8 + j], sh_p[v * 8 + j]);
+        }
+        orow[v] = pack8(o);
+      }
+    }
+  }
+}
+
+// cols[b*n + (g-g0), c*4 + p*2 + q] = bf16(x[b,t,c,2h+p,2w+q] + sem[t,c,2h+p,2w+q])
+template <typename TX, typename TS>
+__global__ void __launch_bounds__(256) patchify_kernel(const TX* __restrict__ x, const TS* __restrict__ sem,
+                                                       bf16* __restrict__ cols, int batch, int T, int C, int Hp, int Wp,
+                                                       int g0, int n) {
+  // one thread per (row, c, p): reads 2 contiguous inputs, writes 2 contiguous outputs
+  const int K = C * 4;
+  const int64_t total = (int64_t)batch * n * C * 2;
+  const int H = 2 * Hp, W = 2 * Wp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // fastest index: token (so global reads along w are coalesced), then p, then c
+    const int tok = (int)(i % n);
+    int64_t r = i / n;
+    const int pp = (int)(r % 2);
+    r /= 2;
+    const int c = (int)(r % C);
+    const int b = (int)(r / C);
+    const int g = g0 + tok;
+    const int hw = Hp * Wp;
+    const int t = g / hw, rem = g - t * hw;
+    const int h = rem / Wp, w = rem - h * Wp;
+    const int64_t src = (((int64_t)t * C + c) * H + (2 * h + pp)) * W + 2 * w;
+    const int64_t xsrc = (int64_t)b * T * C * H * W + src;
+    float v0 = (float)x[xsrc], v1 = (float)x[xsrc + 1];
+    if (sem != nullptr) {
+      // the reference adds in bf16: x (already cast to bf16) + sem (bf16) -> bf16   (dit_video_concat.py:937,991)
+      v0 = __bfloat162float(__float2bfloat16_rn(v0)) + (float)sem[src];
+      v1 = __bfloat162float(__float2bfloat16_rn(v1)) + (float)sem[src + 1];
+    }
+    *reinterpret_cast<uint32_t*>(cols + ((int64_t)b * n + tok) * K + c * 4 + pp * 2) = pack_bf16x2(v0, v1);
+  }
+}
+
+// y[b,n] = act_out(sum_k act_in(x[b,k]) W[n,k] + bias[n]); one warp per output feature, B <= 8
+__device__ __forceinline__ float silu(float v) { return v / (1.0f + __expf(-v)); }
+
+template <int MAXB>
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ x, const bf16* __restrict__ W,
+                                                           const bf16* __restrict__ bias, float* __restrict__ y,
+                                                           int batch, int N, int K, int act_in, int act_out,
+                                                           int round_bf16) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float acc[MAXB];
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+  const uint4* wr = reinterpret_cast<const uint4*>(W + (int64_t)n * K);
+  for (int v = lane; v < (K >> 3); v += 32) {
+    float wv[8];
+    unpack8(wr[v], wv);
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b)
+      if (b < batch) {
+        const float4 x0 = reinterpret_cast<const float4*>(x + (int64_t)b * K)[2 * v];
+        const float4 x1 = reinterpret_cast<const float4*>(x + (int64_t)b * K)[2 * v + 1];
+        float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float xi = xv[j];
+          if (act_in == 1) {
+            xi = silu(xi);
+            if (round_bf16) xi = __bfloat162float(__float2bfloat16_rn(xi));
+          }
+          acc[b] = fmaf(xi, wv[j], acc[b]);
+        }
+      }
+  }
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) acc[b] = warp_sum(acc[b]);
+  if (lane == 0) {
+    const float bv = bias ? __bfloat162float(bias[n]) : 0.f;
+    for (int b = 0; b < batch; ++b) {
+      float v = acc[b] + bv;
+      if (round_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
+      if (act_out == 1) {
+        v = silu(v);
+        if (round_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
+      }
+      y[(int64_t)b * N + n] = v;
+    }
+  }
+}
+
+// [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(max_period) i / half)   (sgm/.../util.py:207-233)
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int batch, int dim,
+                                          float max_period, int round_bf16) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * half) return;
+  const int b = i / half, k = i - b * half;
+  const float freq = expf(-logf(max_period) * (float)k / (float)half);
+  const float arg = t[b] * freq;
+  float c = cosf(arg), s = sinf(arg);
+  if (round_bf16) {
+    c = __bfloat162float(__float2bfloat16_rn(c));
+    s = __bfloat162float(__float2bfloat16_rn(s));
+  }
+  out[(int64_t)b * dim + k] = c;
+  out[(int64_t)b * dim + half + k] = s;
+  if ((dim & 1) && k == 0) out[(int64_t)b * dim + dim - 1] = 0.f;
+}
+
+__global__ void __launch_bounds__(256) sampler_update_kernel(const float* __restrict__ x, const bf16* __restrict__ net_u,
+                                                             const bf16* __restrict__ net_c,
+                                                             const float* __restrict__ old_den,
+                                                             const float* __restrict__ eps, float* __restrict__ x_out,
+                                                             float* __restrict__ den_out, int64_t n, float c_skip,
+                                                             float c_out, float cfg, float m1, float m2, float m3,
+                                                             float m4, float mn, int mode) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float xv = x[i];
+    // same operation order as the reference: net*c_out + x*c_skip (fp32), then x_u + s*(x_c - x_u)
+    const float du = __bfloat162float(net_u[i]) * c_out + xv * c_skip;
+    const float dc = __bfloat162float(net_c[i]) * c_out + xv * c_skip;
+    const float den = du + cfg * (dc - du);
+    float xo;
+    if (mode == 2) {
+      xo = den;
+    } else if (mode == 0) {
+      xo = m1 * xv - m2 * den + mn * eps[i];
+    } else {
+      const float dd = m3 * den - m4 * old_den[i];
+      xo = m1 * xv - m2 * dd + mn * eps[i];
+    }
+    x_out[i] = xo;
+    den_out[i] = den;
+  }
+}
+
+static inline int grid_for(int64_t work_items, int per_block, int max_blocks) {
+  int64_t g = (work_items + per_block - 1) / per_block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace ld
+
+using namespace ld;
+
+extern "C" int ld_layernorm_modulate(const void* x, void* out, const void* w, const void* b, float eps,
+                                     const float* shift_img, const float* scale_img, const float* shift_txt,
+                                     const float* scale_txt, int64_t mod_batch_stride, int batch, int rows_per_batch,
+                                     int tok_offset, int text_len, int D, void* stream) {
+  int rc = check_device();
+  if (rc != LD_OK) return rc;
+  LD_CHECK_ARG(x && out && w && b && shift_img && scale_img && shift_txt && scale_txt, "ld_layernorm_modulate: null pointer");
+  LD_CHECK_ARG(D % 8 == 0 && D > 0 && D <= 2048, "ld_layernorm_modulate: D=%d must be a multiple of 8 and <= 2048", D);
+  LD_CHECK_ARG(batch > 0 && rows_per_batch > 0, "ld_layernorm_modulate: empty input");
+  const int rows = batch * rows_per_batch;
+  const int grid = grid_for(rows, 8, sm_count() * 16);
+  ln_modulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, (const bf16*)w, (const bf16*)b, eps,
+                                                              shift_img, scale_img, shift_txt, scale_txt,
+                                                              mod_batch_stride, rows, rows_per_batch, tok_offset,
+                                                              text_len, D);
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}
+
+extern "C" int ld_final_norm_modulate(const void* x, void* out, const void* w1, const void* b1, float eps1,
+                                      const void* w2, const void* b2, float eps2, const float* shift,
+                                      const float* scale, int64_t mod_batch_stride, int batch, int rows_per_batch,
+                                      int tok_offset, int text_len, int D, void* stream) {
+  int rc = check_device();
+  if (rc != LD_OK) return rc;
+  LD_CHECK_ARG(x && out && w1 && b1 && w2 && b2 && shift && scale, "ld_final_norm_modulate: null pointer");
+  LD_CHECK_ARG(D % 8 == 0 && D > 0 && D <= 2048, "ld_final_norm_modulate: D=%d must be a multiple of 8 and <= 2048", D);
+  int first_img = text_len - tok_offset;
+  if (first_img < 0) first_img = 0;
+  LD_CHECK_ARG(first_img < rows_per_batch, "ld_final_norm_modulate: shard holds no image rows");
+  const int rows = batch * (rows_per_batch - first_img);
+  const int grid = grid_for(rows, 8, sm_count() * 16);
+  final_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, (const bf16*)w1, (const bf16*)b1, eps1,
+                                                             (const bf16*)w2, (const bf16*)b2, eps2, shift, scale,
+                                                             mod_batch_stride, batch, rows_per_batch, first_img, D);
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}
+
+extern "C" int ld_patchify(const void* x, int x_is_f32, const void* sem, int sem_is_f32, void* cols, int batch, int T,
+                           int C, int Hp, int Wp, int g0, int n, void* stream) {
+  int rc = check_device();
+  if (rc != LD_OK) return rc;
+  LD_CHECK_ARG(x && cols, "ld_patchify: null pointer");
+  LD_CHECK_ARG(batch > 0 && T > 0 && C > 0 && Hp > 0 && Wp > 0 && n > 0 && g0 >= 0 && g0 + n <= T * Hp * Wp,
+               "ld_patchify: bad shape");
+  const int64_t total = (int64_t)batch * n * C * 2;
+  const int grid = grid_for(total, 256, sm_count() * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_is_f32) {
+    if (sem && !sem_is_f32)
+      patchify_kernel<float, bf16><<<grid, 256, 0, st>>>((const float*)x, (const bf16*)sem, (bf16*)cols, batch, T, C, Hp, Wp, g0, n);
+    else
+      patchify_kernel<float, float><<<grid, 256, 0, st>>>((const float*)x, (const float*)sem, (bf16*)cols, batch, T, C, Hp, Wp, g0, n);
+  } else {
+    if (sem && sem_is_f32)
+      patchify_kernel<bf16, float><<<grid, 256, 0, st>>>((const bf16*)x, (const float*)sem, (bf16*)cols, batch, T, C, Hp, Wp, g0, n);
+    else
+      patchify_kernel<bf16, bf16><<<grid, 256, 0, st>>>((const bf16*)x, (const bf16*)sem, (bf16*)cols, batch, T, C, Hp, Wp, g0, n);
+  }
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}
+
+extern "C" int ld_small_linear(const float* x, const void* W, const void* bias, float* y, int batch, int N, int K,
+                               int act_in, int act_out, int round_bf16, void* stream) {
+  int rc = check_device();
+  if (rc != LD_OK) return rc;
+  LD_CHECK_ARG(x && W && y, "ld_small_linear: null pointer");
+  LD_CHECK_ARG(batch >= 1 && batch <= 8, "ld_small_linear: batch=%d must be in [1,8]", batch);
+  LD_CHECK_ARG(K % 8 == 0 && N > 0, "ld_small_linear: K=%d must be a multiple of 8", K);
+  const int grid = (N + 7) / 8;
+  if (batch <= 2)
+    small_linear_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)W, (const bf16*)bias, y, batch, N, K, act_in, act_out, round_bf16);
+  else
+    small_linear_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)W, (const bf16*)bias, y, batch, N, K, act_in, act_out, round_bf16);
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}
+
+extern "C" int ld_timestep_embedding(const float* t, float* out, int batch, int dim, float max_period, int round_bf16,
+                                     void* stream) {
+  int rc = check_device();
+  if (rc != LD_OK) return rc;
+  LD_CHECK_ARG(t && out && batch > 0 && dim >= 2, "ld_timestep_embedding: bad arguments");
+  const int n = batch * (dim / 2);
+  timestep_embedding_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(t, out, batch, dim, max_period, round_bf16);
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}
+
+extern "C" int ld_sampler_update(const float* x, const void* net_u, const void* net_c, const float* old_den,
+                                 const float* eps, float* x_out, float* den_out, int64_t n, float c_skip, float c_out,
+                                 float cfg, float m1, float m2, float m3, float m4, float mn, int mode, void* stream) {
+  int rc = check_device();
+  if (rc != LD_OK) return rc;
+  LD_CHECK_ARG(x && net_u && net_c && x_out && den_out && n > 0, "ld_sampler_update: null pointer / empty");
+  LD_CHECK_ARG(mode >= 0 && mode <= 2, "ld_sampler_update: bad mode %d", mode);
+  LD_CHECK_ARG(mode == 2 || eps != nullptr, "ld_sampler_update: eps required");
+  LD_CHECK_ARG(mode != 1 || old_den != nullptr, "ld_sampler_update: old_den required for mode 1");
+  const int grid = grid_for(n, 256, sm_count() * 8);
+  sampler_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)net_u, (const bf16*)net_c, old_den, eps, x_out,
+                                                                 den_out, n, c_skip, c_out, cfg, m1, m2, m3, m4, mn, mode);
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}

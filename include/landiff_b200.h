@@ -1,0 +1,139 @@
+/*
+ * landiff_b200 — C-ABI of the B200-native (sm_100a) DiT hot path for LanDiff's diffusion stage.
+ *
+ * Plain C: pointers are DEVICE pointers unless stated otherwise, sizes are ints, `stream` is a cudaStream_t
+ * passed as void*.  Every entry point returns LD_OK (0) or a negative error code; ld_last_error() gives the
+ * thread-local message.  There is no CPU fallback: on a machine without an sm_100 device every compute entry
+ * point fails with LD_ERR_DEVICE.
+ *
+ * The reference (pure Python, /root/reference) has no FFI; each entry point below names the reference
+ * PyTorch expression it replaces (file:line relative to the reference root).  The Python host in
+ * landiff_b200/ binds these with ctypes and registers them as torch.library custom ops; INTEGRATION.md shows
+ * the binding a reference maintainer would add.
+ *
+ * Layout conventions: activations are row-major bf16 [rows, features]; a "row" is one token of one sample,
+ * rows of sample b occupy [b*rows_per_batch, (b+1)*rows_per_batch).  Token t of a sample is a TEXT token iff
+ * tok_offset + t < text_len (dit_video_concat.py:549-550).  Linear weights keep the nn.Linear layout
+ * [out_features, in_features] bf16 (no copies, no re-packing).
+ */
+#ifndef LANDIFF_B200_H
+#define LANDIFF_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LD_OK 0
+#define LD_ERR_ARG (-1)    /* bad shape / alignment / null pointer */
+#define LD_ERR_CUDA (-2)   /* CUDA runtime / driver error */
+#define LD_ERR_DEVICE (-3) /* no sm_100 device */
+
+const char* ld_last_error(void);
+int ld_abi_version(void);
+/* 0 iff the current device is compute capability 10.x; fills sm_count if non-null. */
+int ld_device_check(int* sm_count);
+
+/* ---- dense contractions: out = epilogue(A[M,K] @ W[N,K]^T), tcgen05/TMEM tiles fed by TMA ------------- */
+enum ld_epilogue {
+  LD_EPI_NONE = 0,        /* out = acc                      control zero_linears, dit_video_concat.py:1234-1237 */
+  LD_EPI_BIAS = 1,        /* out = acc + bias               text_proj :55-58 (with row remap into hidden)       */
+  LD_EPI_BIAS_GELU = 2,   /* out = gelu_tanh(acc + bias)    SAT MLP dense_h_to_4h + activation, :612, :731-733  */
+  LD_EPI_GATED_RESID = 3, /* out = resid + gate[seg]*(acc+bias) (+ add2)   :593-598, :619-624, :1357-1370       */
+  LD_EPI_QKV = 4,         /* split Q|K|V, per-head LayerNorm(64) on Q,K, head-major store   :636-664 + SAT      */
+  LD_EPI_BIAS_POS = 5,    /* out = acc + bias + pos[token]  patch-embed conv as GEMM :47-62, pos add :227-231   */
+  LD_EPI_UNPATCHIFY = 6   /* out[b,t,c,2h+p,2w+q] = acc + bias   final linear + unpatchify :392-410, :453-456   */
+};
+
+typedef struct ld_gemm_args {
+  int32_t M, N, K;              /* K % 64 == 0; N % tile_n == 0 (tile_n: 192 for N%192==0, else 128, else 64) */
+  int32_t epilogue;             /* enum ld_epilogue */
+  const void* A;                /* [M, K] bf16 row-major */
+  const void* W;                /* [N, K] bf16 row-major (nn.Linear weight) */
+  const void* bias;             /* [N] bf16 or NULL */
+  void* out;                    /* bf16; row stride ld_out elements (ignored by QKV) */
+  int64_t ld_out;
+  /* row bookkeeping: A row r belongs to sample b = r / rows_per_batch, token tok_offset + r % rows_per_batch;
+     it is written to out row b*out_rows_per_batch + out_row_offset + r % rows_per_batch */
+  int32_t rows_per_batch, out_rows_per_batch, out_row_offset;
+  int32_t tok_offset, text_len;
+  /* GATED_RESID: resid/add2 are indexed like out; gate_* point at sample 0's fp32 [N] vectors */
+  const void* resid;
+  const void* add2;
+  const float* gate_img;
+  const float* gate_txt;
+  int64_t mod_batch_stride;     /* floats between consecutive samples' modulation vectors */
+  /* QKV: N = 3*heads*64.  q/k/v are [B, heads, qkv_rows, 64] bf16; token t lands on row qkv_row_offset + t.
+     Q is additionally multiplied by q_scale (softmax scale * log2 e) after its LayerNorm. */
+  void* q; void* k; void* v;
+  const void* q_ln_w; const void* q_ln_b; const void* k_ln_w; const void* k_ln_b; /* bf16 [64] */
+  float ln_eps, q_scale;
+  int32_t heads, qkv_rows, qkv_row_offset;
+  /* BIAS_POS: pos is bf16 [>= text_len + image tokens, N]; the row added is pos[tok_offset + t] */
+  const void* pos;
+  /* UNPATCHIFY: out is bf16 [B, T, C, 2*Hp, 2*Wp]; image token index g = tok_offset + t - text_len */
+  int32_t T, Hp, Wp, C;
+} ld_gemm_args;
+
+int ld_gemm_bf16(const ld_gemm_args* args, void* stream);
+
+/* ---- full (non-causal) self-attention, head_dim 64, flash-style online softmax on tcgen05 ------------- */
+/* q: [BH, q_rows, 64], k/v: [BH, kv_rows, 64] bf16 (q pre-multiplied by scale*log2e, see LD_EPI_QKV).
+   Uses q rows [0,nq) and kv rows [0,nkv).  out: bf16 [B, nq, heads*64] (token-major, ready for `dense`).
+   If lse != NULL also writes fp32 log2-sum-exp [BH, nq] and, when out_f32 != NULL, the normalised fp32 output
+   [BH, nq, 64] (used by the ring merge).  Replaces SAT attention_fn_default -> F.scaled_dot_product_attention
+   reached through dit_video_concat.py:655-664. */
+int ld_attention_bf16(const void* q, const void* k, const void* v, void* out, float* lse, float* out_f32,
+                      int batch, int heads, int nq, int q_rows, int nkv, int kv_rows, int variant, void* stream);
+
+/* merge two partial attention results (ring hop):  (o_acc, lse_acc) <- merge((o_acc, lse_acc), (o_new, lse_new)).
+   o_*: fp32 [BH, nq, 64]; lse_*: fp32 [BH, nq].  If out_bf16 != NULL also writes bf16 [B, nq, heads*64]. */
+int ld_attention_merge(float* o_acc, float* lse_acc, const float* o_new, const float* lse_new, void* out_bf16,
+                       int batch, int heads, int nq, void* stream);
+
+/* ---- fused memory-bound row kernels ------------------------------------------------------------------- */
+/* out = LayerNorm(x; w, b, eps) * (1 + scale[seg]) + shift[seg]   (dit_video_concat.py:577-586, 601-611, :388)
+   x,out: bf16 [B*rows_per_batch, D]; w,b: bf16 [D]; shift_x / scale_x: fp32 [D] of sample 0. D % 8 == 0, D <= 2048 */
+int ld_layernorm_modulate(const void* x, void* out, const void* w, const void* b, float eps,
+                          const float* shift_img, const float* scale_img, const float* shift_txt,
+                          const float* scale_txt, int64_t mod_batch_stride, int batch, int rows_per_batch,
+                          int tok_offset, int text_len, int D, void* stream);
+
+/* final layer front half: y = LN2(LN1(x[image rows]); eps2) * (1 + scale) + shift  -> bf16 [B*n_img, D]
+   (SAT final_layernorm + FinalLayerMixin.final_forward, dit_video_concat.py:442-452).  x: [B, rows_per_batch, D];
+   image rows are those with tok_offset + t >= text_len. */
+int ld_final_norm_modulate(const void* x, void* out, const void* w1, const void* b1, float eps1, const void* w2,
+                           const void* b2, float eps2, const float* shift, const float* scale,
+                           int64_t mod_batch_stride, int batch, int rows_per_batch, int tok_offset, int text_len,
+                           int D, void* stream);
+
+/* im2col for the 2x2/stride-2 patch conv: cols[b*n_img + g, c*4 + p*2 + q] = bf16(x[b,t,c,2h+p,2w+q] (+ sem[t,c,..]))
+   x: fp32 or bf16 [B,T,C,2Hp,2Wp] (x_is_f32), sem: bf16/fp32 [1,T,C,2Hp,2Wp] or NULL (same dtype flag sem_is_f32).
+   Only image tokens g in [g0, g0+n) are produced (sequence shard).  dit_video_concat.py:47-54, :991 */
+int ld_patchify(const void* x, int x_is_f32, const void* sem, int sem_is_f32, void* cols, int batch, int T, int C,
+                int Hp, int Wp, int g0, int n, void* stream);
+
+/* y[b, n] = act_out( sum_k act_in(x[b,k]) * W[n,k] + bias[n] ), tiny-batch GEMV (B <= 8), fp32 in/out, bf16 W.
+   act codes: 0 none, 1 SiLU.  time_embed :764-768, adaLN_modulation :510-515/:555, final adaLN :434-436 */
+int ld_small_linear(const float* x, const void* W, const void* bias, float* y, int batch, int N, int K, int act_in,
+                    int act_out, int round_bf16, void* stream);
+
+/* sinusoidal timestep embedding, [cos | sin] (sgm/modules/diffusionmodules/util.py:207-233) -> fp32 [B, dim] */
+int ld_timestep_embedding(const float* t, float* out, int batch, int dim, float max_period, int round_bf16,
+                          void* stream);
+
+/* fused denoiser scaling + CFG + DPM-Solver++(2M) SDE update, all fp32, n elements:
+     den_u = c_out*net_u + c_skip*x ; den_c likewise        (denoiser.py:38-41, denoiser_scaling.py:62-70)
+     den   = den_u + cfg*(den_c - den_u)                     (guiders.py:75-79, sampling_utils.py:8-13)
+     mode 0 (first step):  x' = m1*x - m2*den + mn*eps                        (sampling.py:771-774)
+     mode 1 (middle):      x' = m1*x - m2*(m3*den - m4*old) + mn*eps          (sampling.py:776-781)
+     mode 2 (last):        x' = den                                           (sampling.py:750-751)
+   net_u/net_c: bf16 network outputs; x, old, eps, x_out, den_out: fp32. */
+int ld_sampler_update(const float* x, const void* net_u, const void* net_c, const float* old_den,
+                      const float* eps, float* x_out, float* den_out, int64_t n, float c_skip, float c_out,
+                      float cfg, float m1, float m2, float m3, float m4, float mn, int mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

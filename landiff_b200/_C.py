@@ -1,0 +1,87 @@
+"""ctypes binding of the C-ABI in include/landiff_b200.h.
+
+The shared library is built in-tree by landiff_b200.build (nvcc, sm_100a).  There is NO fallback: if the
+library is missing it is built; if it cannot be built or loaded this module raises.  Every compute entry
+point fails with LD_ERR_DEVICE on a machine without an sm_100 GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from . import build as _build
+
+LD_OK = 0
+
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_GATED_RESID, EPI_QKV, EPI_BIAS_POS, EPI_UNPATCHIFY = range(7)
+
+
+class GemmArgs(C.Structure):
+    """Mirror of `ld_gemm_args` (include/landiff_b200.h)."""
+
+    _fields_ = [
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("epilogue", C.c_int32),
+        ("A", C.c_void_p), ("W", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p),
+        ("ld_out", C.c_int64),
+        ("rows_per_batch", C.c_int32), ("out_rows_per_batch", C.c_int32), ("out_row_offset", C.c_int32),
+        ("tok_offset", C.c_int32), ("text_len", C.c_int32),
+        ("resid", C.c_void_p), ("add2", C.c_void_p), ("gate_img", C.c_void_p), ("gate_txt", C.c_void_p),
+        ("mod_batch_stride", C.c_int64),
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+        ("q_ln_w", C.c_void_p), ("q_ln_b", C.c_void_p), ("k_ln_w", C.c_void_p), ("k_ln_b", C.c_void_p),
+        ("ln_eps", C.c_float), ("q_scale", C.c_float),
+        ("heads", C.c_int32), ("qkv_rows", C.c_int32), ("qkv_row_offset", C.c_int32),
+        ("pos", C.c_void_p),
+        ("T", C.c_int32), ("Hp", C.c_int32), ("Wp", C.c_int32), ("C", C.c_int32),
+    ]
+
+
+# name -> (restype, argtypes); the CPU test-suite checks every one of these is exported.
+_vp, _i, _f, _i64, _fp = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_void_p
+SIGNATURES = {
+    "ld_last_error": (C.c_char_p, []),
+    "ld_abi_version": (C.c_int, []),
+    "ld_device_check": (C.c_int, [C.POINTER(C.c_int)]),
+    "ld_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "ld_attention_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ld_attention_merge": (C.c_int, [_fp, _fp, _fp, _fp, _vp, _i, _i, _i, _vp]),
+    "ld_layernorm_modulate": (C.c_int, [_vp, _vp, _vp, _vp, _f, _fp, _fp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "ld_final_norm_modulate": (C.c_int, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _f, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "ld_patchify": (C.c_int, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ld_small_linear": (C.c_int, [_fp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ld_timestep_embedding": (C.c_int, [_fp, _fp, _i, _i, _f, _i, _vp]),
+    "ld_sampler_update": (C.c_int, [_fp, _vp, _vp, _fp, _fp, _fp, _fp, _i64] + [_f] * 8 + [_i, _vp]),
+}
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Build (if stale/missing) and load the library; bind signatures.  Raises on any failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not path.exists():
+        path = _build.build()
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class LanDiffB200Error(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != LD_OK:
+        msg = load().ld_last_error().decode(errors="replace")
+        raise LanDiffB200Error(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,272 @@
+"""Tensor-level wrappers over the C-ABI (shape / dtype / contiguity / device checks live here, the C side only
+sees pointers and sizes).  All kernels are enqueued on torch's current CUDA stream.
+
+The same functions are also registered as `torch.ops.landiff_b200.*` custom ops (see `register_torch_ops`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+
+from . import _C
+from ._C import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_POS, EPI_GATED_RESID, EPI_NONE, EPI_QKV, EPI_UNPATCHIFY,
+                 GemmArgs, check)
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name: str, contiguous: bool = True) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (landiff_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def device_check() -> int:
+    sms = C.c_int(0)
+    check(_C.load().ld_device_check(C.byref(sms)), "ld_device_check")
+    return sms.value
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, epilogue: int, bias: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None, rows_per_batch: Optional[int] = None, out_rows_per_batch: Optional[int] = None,
+         out_row_offset: int = 0, tok_offset: int = 0, text_len: int = 0, resid: Optional[torch.Tensor] = None,
+         add2: Optional[torch.Tensor] = None, gate_img: Optional[torch.Tensor] = None,
+         gate_txt: Optional[torch.Tensor] = None, mod_batch_stride: int = 0, qkv=None, qk_ln=None, ln_eps: float = 1e-6,
+         q_scale: float = 1.0, heads: int = 0, qkv_row_offset: int = 0, pos: Optional[torch.Tensor] = None,
+         patch_grid=None) -> Optional[torch.Tensor]:
+    """out = epilogue(a @ w.T).  a: [M,K] bf16, w: [N,K] bf16.  See include/landiff_b200.h for the epilogues."""
+    _chk(a, BF16, "a")
+    _chk(w, BF16, "w")
+    M, K = a.shape
+    N, K2 = w.shape
+    if K != K2:
+        raise ValueError(f"gemm: inner dims differ ({K} vs {K2})")
+    g = GemmArgs()
+    g.M, g.N, g.K, g.epilogue = M, N, K, epilogue
+    g.A, g.W = a.data_ptr(), w.data_ptr()
+    if bias is not None:
+        _chk(bias, BF16, "bias")
+        if bias.numel() != N:
+            raise ValueError("gemm: bias size")
+        g.bias = bias.data_ptr()
+    g.rows_per_batch = rows_per_batch or M
+    g.out_rows_per_batch = out_rows_per_batch if out_rows_per_batch is not None else g.rows_per_batch
+    g.out_row_offset, g.tok_offset, g.text_len = out_row_offset, tok_offset, text_len
+    ret = None
+    if epilogue == EPI_QKV:
+        q, k, v = qkv
+        for n_, t_ in (("q", q), ("k", k), ("v", v)):
+            _chk(t_, BF16, n_)
+            if t_.dim() != 4 or t_.shape[-1] != 64 or t_.shape[1] != heads:
+                raise ValueError(f"gemm: {n_} must be [B, heads, rows, 64]")
+        if not (q.shape[2] == k.shape[2] == v.shape[2]):
+            raise ValueError("gemm: q/k/v row counts differ")
+        qw, qb, kw, kb = qk_ln
+        for t_ in (qw, qb, kw, kb):
+            _chk(t_, BF16, "qk_ln")
+        g.q, g.k, g.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+        g.q_ln_w, g.q_ln_b, g.k_ln_w, g.k_ln_b = qw.data_ptr(), qb.data_ptr(), kw.data_ptr(), kb.data_ptr()
+        g.ln_eps, g.q_scale = ln_eps, q_scale
+        g.heads, g.qkv_rows, g.qkv_row_offset = heads, q.shape[2], qkv_row_offset
+    else:
+        if epilogue == EPI_UNPATCHIFY:
+            if out is None:
+                raise ValueError("gemm: UNPATCHIFY needs out")
+            T, Hp, Wp, Cc = patch_grid
+            g.T, g.Hp, g.Wp, g.C = T, Hp, Wp, Cc
+            _chk(out, BF16, "out")
+            g.ld_out = 0
+        else:
+            if out is None:
+                out = torch.empty((M, N), dtype=BF16, device=a.device)
+            _chk(out, BF16, "out", contiguous=False)
+            if out.stride(-1) != 1:
+                raise ValueError("gemm: out must have unit inner stride")
+            g.ld_out = out.stride(0) if out.dim() == 2 else N
+        g.out = out.data_ptr()
+        ret = out
+        if epilogue == EPI_GATED_RESID:
+            _chk(resid, BF16, "resid", contiguous=False)
+            _chk(gate_img, F32, "gate_img", contiguous=False)
+            _chk(gate_txt, F32, "gate_txt", contiguous=False)
+            g.resid, g.gate_img, g.gate_txt = resid.data_ptr(), gate_img.data_ptr(), gate_txt.data_ptr()
+            g.mod_batch_stride = mod_batch_stride
+            if add2 is not None:
+                _chk(add2, BF16, "add2", contiguous=False)
+                g.add2 = add2.data_ptr()
+        if epilogue == EPI_BIAS_POS:
+            _chk(pos, BF16, "pos")
+            g.pos = pos.data_ptr()
+    check(_C.load().ld_gemm_bf16(C.byref(g), _stream()), "ld_gemm_bf16")
+    return ret
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, nq: Optional[int] = None, nkv: Optional[int] = None,
+              out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
+              out_f32: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
+    """softmax(q k^T / 8) v for q,k,v [B, H, rows, 64] bf16 -> [B, nq, H*64] bf16 (full attention)."""
+    for n_, t_ in (("q", q), ("k", k), ("v", v)):
+        _chk(t_, BF16, n_)
+        if t_.dim() != 4 or t_.shape[-1] != 64:
+            raise ValueError(f"attention: {n_} must be [B, H, rows, 64]")
+    B, H, q_rows, _ = q.shape
+    kv_rows = k.shape[2]
+    nq = q_rows if nq is None else nq
+    nkv = kv_rows if nkv is None else nkv
+    if out is None:
+        out = torch.empty((B, nq, H * 64), dtype=BF16, device=q.device)
+    _chk(out, BF16, "out")
+    if lse is not None:
+        _chk(lse, F32, "lse")
+    if out_f32 is not None:
+        _chk(out_f32, F32, "out_f32")
+    check(_C.load().ld_attention_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _ptr(lse), _ptr(out_f32),
+                                      B, H, nq, q_rows, nkv, kv_rows, variant, _stream()), "ld_attention_bf16")
+    return out
+
+
+def attention_merge(o_acc, lse_acc, o_new, lse_new, out_bf16, batch, heads, nq) -> None:
+    for t_ in (o_acc, lse_acc, o_new, lse_new):
+        _chk(t_, F32, "merge operand")
+    check(_C.load().ld_attention_merge(o_acc.data_ptr(), lse_acc.data_ptr(), o_new.data_ptr(), lse_new.data_ptr(),
+                                       _ptr(out_bf16), batch, heads, nq, _stream()), "ld_attention_merge")
+
+
+def layernorm_modulate(x, w, b, eps, shift_img, scale_img, shift_txt, scale_txt, mod_batch_stride, batch,
+                       rows_per_batch, tok_offset, text_len, out=None):
+    _chk(x, BF16, "x")
+    D = x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    for t_ in (shift_img, scale_img, shift_txt, scale_txt):
+        _chk(t_, F32, "modulation", contiguous=False)
+    check(_C.load().ld_layernorm_modulate(x.data_ptr(), out.data_ptr(), w.data_ptr(), b.data_ptr(), eps,
+                                          shift_img.data_ptr(), scale_img.data_ptr(), shift_txt.data_ptr(),
+                                          scale_txt.data_ptr(), mod_batch_stride, batch, rows_per_batch, tok_offset,
+                                          text_len, D, _stream()), "ld_layernorm_modulate")
+    return out
+
+
+def final_norm_modulate(x, w1, b1, eps1, w2, b2, eps2, shift, scale, mod_batch_stride, batch, rows_per_batch,
+                        tok_offset, text_len, out=None):
+    _chk(x, BF16, "x")
+    D = x.shape[-1]
+    first_img = max(text_len - tok_offset, 0)
+    n_img = rows_per_batch - first_img
+    if out is None:
+        out = torch.empty((batch * n_img, D), dtype=BF16, device=x.device)
+    check(_C.load().ld_final_norm_modulate(x.data_ptr(), out.data_ptr(), w1.data_ptr(), b1.data_ptr(), eps1,
+                                           w2.data_ptr(), b2.data_ptr(), eps2, shift.data_ptr(), scale.data_ptr(),
+                                           mod_batch_stride, batch, rows_per_batch, tok_offset, text_len, D, _stream()),
+          "ld_final_norm_modulate")
+    return out
+
+
+def patchify(x: torch.Tensor, sem: Optional[torch.Tensor], g0: int = 0, n: Optional[int] = None, out=None):
+    """x: [B,T,C,H,W] fp32/bf16; sem: [1,T,C,H,W] or None -> cols [B*n, C*4] bf16 for image tokens [g0, g0+n)."""
+    if x.dtype not in (F32, BF16):
+        raise TypeError("patchify: x must be fp32 or bf16")
+    _chk(x, x.dtype, "x")
+    B, T, Cc, H, W = x.shape
+    Hp, Wp = H // 2, W // 2
+    n = T * Hp * Wp - g0 if n is None else n
+    if sem is not None:
+        if sem.dtype not in (F32, BF16):
+            raise TypeError("patchify: sem must be fp32 or bf16")
+        _chk(sem, sem.dtype, "sem")
+        if sem.numel() != T * Cc * H * W:
+            raise ValueError("patchify: sem must be [1,T,C,H,W]")
+    if out is None:
+        out = torch.empty((B * n, Cc * 4), dtype=BF16, device=x.device)
+    check(_C.load().ld_patchify(x.data_ptr(), int(x.dtype == F32), _ptr(sem), int(sem is not None and sem.dtype == F32),
+                                out.data_ptr(), B, T, Cc, Hp, Wp, g0, n, _stream()), "ld_patchify")
+    return out
+
+
+def small_linear(x, w, bias, act_in=0, act_out=0, round_bf16=True, out=None):
+    _chk(x, F32, "x")
+    _chk(w, BF16, "w")
+    Bn, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((Bn, N), dtype=F32, device=x.device)
+    _chk(out, F32, "out")
+    check(_C.load().ld_small_linear(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), Bn, N, K, act_in, act_out,
+                                    int(round_bf16), _stream()), "ld_small_linear")
+    return out
+
+
+def timestep_embedding(t, dim, max_period=10000.0, round_bf16=True, out=None):
+    _chk(t, F32, "t")
+    Bn = t.numel()
+    if out is None:
+        out = torch.empty((Bn, dim), dtype=F32, device=t.device)
+    check(_C.load().ld_timestep_embedding(t.data_ptr(), out.data_ptr(), Bn, dim, max_period, int(round_bf16), _stream()),
+          "ld_timestep_embedding")
+    return out
+
+
+def sampler_update(x, net_u, net_c, old_den, eps, *, c_skip, c_out, cfg, m1=0.0, m2=0.0, m3=0.0, m4=0.0, mn=0.0, mode=0,
+                   x_out=None, den_out=None):
+    _chk(x, F32, "x")
+    _chk(net_u, BF16, "net_u")
+    _chk(net_c, BF16, "net_c")
+    n = x.numel()
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    if den_out is None:
+        den_out = torch.empty_like(x)
+
+    def fin(v):  # the reference's scalars may be +-inf-derived limits; pass them through as floats
+        return float(v)
+
+    check(_C.load().ld_sampler_update(x.data_ptr(), net_u.data_ptr(), net_c.data_ptr(), _ptr(old_den), _ptr(eps),
+                                      x_out.data_ptr(), den_out.data_ptr(), n, fin(c_skip), fin(c_out), fin(cfg), fin(m1),
+                                      fin(m2), fin(m3), fin(m4), fin(mn), mode, _stream()), "ld_sampler_update")
+    return x_out, den_out
+
+
+_registered = False
+
+
+def register_torch_ops() -> None:
+    """Expose the C-ABI entry points as `torch.ops.landiff_b200.*` (thin custom ops over the ctypes calls)."""
+    global _registered
+    if _registered:
+        return
+    lib = torch.library.Library("landiff_b200", "DEF")
+    lib.define("attention(Tensor q, Tensor k, Tensor v, int variant=0) -> Tensor")
+    lib.define("linear(Tensor a, Tensor w, Tensor? bias, int epilogue=1) -> Tensor")
+    lib.define("sampler_update(Tensor x, Tensor net_u, Tensor net_c, Tensor? old_den, Tensor? eps, float c_skip, "
+               "float c_out, float cfg, float m1, float m2, float m3, float m4, float mn, int mode) -> (Tensor, Tensor)")
+
+    def _attention(q, k, v, variant=0):
+        return attention(q, k, v, variant=variant)
+
+    def _linear(a, w, bias, epilogue=1):
+        return gemm(a, w, epilogue=epilogue, bias=bias)
+
+    def _sampler_update(x, net_u, net_c, old_den, eps, c_skip, c_out, cfg, m1, m2, m3, m4, mn, mode):
+        return sampler_update(x, net_u, net_c, old_den, eps, c_skip=c_skip, c_out=c_out, cfg=cfg, m1=m1, m2=m2, m3=m3,
+                              m4=m4, mn=mn, mode=mode)
+
+    lib.impl("attention", _attention, "CUDA")
+    lib.impl("linear", _linear, "CUDA")
+    lib.impl("sampler_update", _sampler_update, "CUDA")
+    register_torch_ops._lib = lib  # keep alive
+    _registered = True

@@ -1,0 +1,195 @@
+"""First-contact GPU probe: runs each hand-written kernel on small shapes against a torch fp32 restatement and
+prints error metrics (no asserts) so one gpurun call tells which hardware-encoding hypotheses hold.
+
+usage: python tools/gpu_probe.py <case> [...]     cases: gemm attn0 attn1 rows all
+"""
+import sys
+import time
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from landiff_b200 import ops  # noqa: E402
+from landiff_b200._C import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_POS, EPI_GATED_RESID, EPI_NONE, EPI_QKV,  # noqa: E402
+                             EPI_UNPATCHIFY)
+
+dev = "cuda"
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def report(name, got, ref):
+    ok = torch.isfinite(got.float()).all().item()
+    r = rel(got, ref)
+    mx = (got.float() - ref.float()).abs().max().item()
+    print(f"  {name:44s} rel_l2={r:.3e} max_abs={mx:.3e} finite={ok} {'OK' if (ok and r < 1e-2) else 'BAD'}", flush=True)
+
+
+def probe_gemm():
+    torch.manual_seed(0)
+    for (M, N, K) in [(128, 192, 64), (128, 192, 128), (300, 192, 128), (1000, 1920, 1920), (515, 256, 192), (130, 64, 1920),
+                      (4096, 7680, 1920), (2000, 1920, 7680)]:
+        a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+        w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+        out = ops.gemm(a, w, epilogue=EPI_NONE)
+        torch.cuda.synchronize()
+        report(f"gemm NONE {M}x{N}x{K}", out, a.float() @ w.float().T)
+    M, N, K = 2 * 443, 1920, 1920
+    a = (torch.randn(M, K, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    bias = (torch.randn(N, device=dev) * 0.1).bfloat16()
+    ref = a.float() @ w.float().T + bias.float()
+    report("gemm BIAS", ops.gemm(a, w, epilogue=EPI_BIAS, bias=bias), ref)
+    report("gemm BIAS_GELU", ops.gemm(a, w, epilogue=EPI_BIAS_GELU, bias=bias),
+           torch.nn.functional.gelu(ref, approximate="tanh"))
+    # gated residual, 2 samples x 443 tokens, 226... use text_len 100
+    B, R, TL = 2, 443, 100
+    mod = torch.randn(B, 12, N, device=dev) * 0.5
+    resid = torch.randn(M, N, device=dev).bfloat16()
+    add2 = torch.randn(M, N, device=dev).bfloat16()
+    gate_img, gate_txt = mod[:, 2], mod[:, 8]
+    tok = torch.arange(M, device=dev) % R
+    bidx = torch.arange(M, device=dev) // R
+    gsel = torch.where((tok < TL)[:, None], gate_txt[bidx], gate_img[bidx])
+    for use_add2 in (False, True):
+        out = ops.gemm(a, w, epilogue=EPI_GATED_RESID, bias=bias, rows_per_batch=R, text_len=TL, resid=resid,
+                       add2=add2 if use_add2 else None, gate_img=gate_img, gate_txt=gate_txt, mod_batch_stride=12 * N)
+        r = resid.float() + gsel * ref + (add2.float() if use_add2 else 0)
+        report(f"gemm GATED_RESID add2={use_add2}", out, r)
+    # in-place variant (out aliases resid)
+    res2 = resid.clone()
+    ops.gemm(a, w, epilogue=EPI_GATED_RESID, bias=bias, rows_per_batch=R, text_len=TL, resid=res2, out=res2,
+             gate_img=gate_img, gate_txt=gate_txt, mod_batch_stride=12 * N)
+    report("gemm GATED_RESID in-place", res2, resid.float() + gsel * ref)
+    # QKV
+    H = 6
+    N3 = 3 * H * 64
+    wq = (torch.randn(N3, K, device=dev) * 0.05).bfloat16()
+    bq = (torch.randn(N3, device=dev) * 0.1).bfloat16()
+    lnp = [(1 + 0.1 * torch.randn(64, device=dev)).bfloat16(), (0.1 * torch.randn(64, device=dev)).bfloat16(),
+           (1 + 0.1 * torch.randn(64, device=dev)).bfloat16(), (0.1 * torch.randn(64, device=dev)).bfloat16()]
+    q = torch.zeros(B, H, R + 5, 64, device=dev, dtype=torch.bfloat16)
+    k = torch.zeros_like(q)
+    v = torch.zeros_like(q)
+    ops.gemm(a, wq, epilogue=EPI_QKV, bias=bq, rows_per_batch=R, qkv=(q, k, v), qk_ln=lnp, ln_eps=1e-6, heads=H,
+             qkv_row_offset=5)
+    qkv_ref = (a.float() @ wq.float().T + bq.float()).bfloat16().float().view(B, R, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ln = torch.nn.functional.layer_norm
+    report("gemm QKV q", q[:, :, 5:], ln(qkv_ref[0], (64,), lnp[0].float(), lnp[1].float(), 1e-6))
+    report("gemm QKV k", k[:, :, 5:], ln(qkv_ref[1], (64,), lnp[2].float(), lnp[3].float(), 1e-6))
+    report("gemm QKV v", v[:, :, 5:], qkv_ref[2])
+    # BIAS_POS with row remap: M rows of image tokens written after TL text rows
+    pos = torch.randn(TL + R, N, device=dev).bfloat16()
+    hidden = torch.zeros(B, TL + R, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, epilogue=EPI_BIAS_POS, bias=bias, out=hidden.view(-1, N), rows_per_batch=R, out_rows_per_batch=TL + R,
+             out_row_offset=TL, tok_offset=TL, text_len=TL, pos=pos)
+    report("gemm BIAS_POS remap", hidden[:, TL:], ref.view(B, R, N) + pos[TL:].float())
+    print("  text rows untouched:", bool((hidden[:, :TL] == 0).all()))
+    # UNPATCHIFY: T=2,Hp=3,Wp=5 -> 30 image tokens per sample
+    T, Hp, Wp, Cc = 2, 3, 5, 16
+    n_img = T * Hp * Wp
+    a2 = (torch.randn(B * n_img, K, device=dev) * 0.5).bfloat16()
+    w2 = (torch.randn(64, K, device=dev) * 0.05).bfloat16()
+    b2 = (torch.randn(64, device=dev) * 0.1).bfloat16()
+    out = torch.zeros(B, T, Cc, 2 * Hp, 2 * Wp, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a2, w2, epilogue=EPI_UNPATCHIFY, bias=b2, out=out, rows_per_batch=n_img, tok_offset=TL, text_len=TL,
+             patch_grid=(T, Hp, Wp, Cc))
+    y = (a2.float() @ w2.float().T + b2.float()).view(B, T, Hp, Wp, Cc, 2, 2)
+    report("gemm UNPATCHIFY", out, y.permute(0, 1, 4, 2, 5, 3, 6).reshape(B, T, Cc, 2 * Hp, 2 * Wp))
+
+
+def probe_attn(variant):
+    torch.manual_seed(1)
+    for (B, H, nq, nkv) in [(1, 1, 128, 128), (1, 1, 256, 128), (1, 2, 300, 300), (2, 3, 886, 886), (1, 2, 500, 1000),
+                            (1, 4, 4444, 17776)]:
+        q = torch.randn(B, H, nq, 64, device=dev).bfloat16()
+        k = torch.randn(B, H, nkv, 64, device=dev).bfloat16()
+        v = torch.randn(B, H, nkv, 64, device=dev).bfloat16()
+        lse = torch.zeros(B * H, nq, device=dev)
+        of = torch.zeros(B * H, nq, 64, device=dev)
+        t0 = time.time()
+        out = ops.attention(q, k, v, variant=variant, lse=lse, out_f32=of)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+        report(f"attn v{variant} B{B} H{H} nq{nq} nkv{nkv} ({dt*1e3:.1f} ms)", out, ref.permute(0, 2, 1, 3).reshape(B, nq, H * 64))
+        s = (q.float() @ k.float().transpose(-1, -2)) * 0.125
+        lse_ref = torch.logsumexp(s, -1) * 1.4426950408889634
+        report("   lse", lse, lse_ref.view(B * H, nq))
+        report("   out_f32", of, ref.reshape(B * H, nq, 64))
+
+
+def probe_rows():
+    torch.manual_seed(2)
+    B, R, TL, D = 2, 443, 100, 1920
+    x = torch.randn(B * R, D, device=dev).bfloat16()
+    w = (1 + 0.1 * torch.randn(D, device=dev)).bfloat16()
+    b = (0.1 * torch.randn(D, device=dev)).bfloat16()
+    mod = torch.randn(B, 12, D, device=dev) * 0.5
+    out = ops.layernorm_modulate(x, w, b, 1e-5, mod[:, 0], mod[:, 1], mod[:, 6], mod[:, 7], 12 * D, B, R, 0, TL)
+    ln = torch.nn.functional.layer_norm(x.float(), (D,), w.float(), b.float(), 1e-5).view(B, R, D)
+    tok = torch.arange(R, device=dev)
+    shift = torch.where((tok < TL)[None, :, None], mod[:, 6][:, None], mod[:, 0][:, None])
+    scale = torch.where((tok < TL)[None, :, None], mod[:, 7][:, None], mod[:, 1][:, None])
+    report("layernorm_modulate", out.view(B, R, D), ln * (1 + scale) + shift)
+    w2 = (1 + 0.1 * torch.randn(D, device=dev)).bfloat16()
+    b2 = (0.1 * torch.randn(D, device=dev)).bfloat16()
+    fm = torch.randn(B, 2, D, device=dev) * 0.5
+    out = ops.final_norm_modulate(x, w, b, 1e-5, w2, b2, 1e-6, fm[:, 0], fm[:, 1], 2 * D, B, R, 0, TL)
+    l1 = torch.nn.functional.layer_norm(x.float(), (D,), w.float(), b.float(), 1e-5).bfloat16().float().view(B, R, D)[:, TL:]
+    l2 = torch.nn.functional.layer_norm(l1, (D,), w2.float(), b2.float(), 1e-6)
+    report("final_norm_modulate", out.view(B, R - TL, D), l2 * (1 + fm[:, 1][:, None]) + fm[:, 0][:, None])
+    T, Cc, Hp, Wp = 2, 16, 15, 22
+    xin = torch.randn(B, T, Cc, 2 * Hp, 2 * Wp, device=dev)
+    sem = (torch.randn(1, T, Cc, 2 * Hp, 2 * Wp, device=dev) * 0.1).bfloat16()
+    cols = ops.patchify(xin, sem)
+    xs = (xin.bfloat16().float() + sem.float())
+    ref = xs.view(B, T, Cc, Hp, 2, Wp, 2).permute(0, 1, 3, 5, 2, 4, 6).reshape(B * T * Hp * Wp, Cc * 4)
+    report("patchify (+sem)", cols, ref)
+    cols = ops.patchify(xin, None, g0=100, n=300)
+    ref = xin.view(B, T, Cc, Hp, 2, Wp, 2).permute(0, 1, 3, 5, 2, 4, 6).reshape(B, T * Hp * Wp, Cc * 4)[:, 100:400]
+    report("patchify shard", cols.view(B, 300, 64), ref)
+    xe = torch.randn(B, 512, device=dev)
+    wl = (torch.randn(23040, 512, device=dev) * 0.05).bfloat16()
+    bl = (torch.randn(23040, device=dev) * 0.1).bfloat16()
+    y = ops.small_linear(xe, wl, bl, act_in=1, round_bf16=False)
+    report("small_linear silu-in", y, torch.nn.functional.silu(xe) @ wl.float().T + bl.float())
+    t = torch.tensor([999.0, 19.0], device=dev)
+    te = ops.timestep_embedding(t, 1920, round_bf16=False)
+    half = 960
+    freqs = torch.exp(-torch.log(torch.tensor(10000.0)) * torch.arange(half, dtype=torch.float32) / half).to(dev)
+    args = t[:, None] * freqs[None]
+    report("timestep_embedding", te, torch.cat([torch.cos(args), torch.sin(args)], -1))
+    n = 13 * 16 * 60 * 90
+    xx, old, eps = torch.randn(n, device=dev), torch.randn(n, device=dev), torch.randn(n, device=dev)
+    nu, nc = torch.randn(n, device=dev).bfloat16(), torch.randn(n, device=dev).bfloat16()
+    kw = dict(c_skip=0.3, c_out=-0.95, cfg=4.5, m1=0.9, m2=-0.2, m3=1.7, m4=0.7, mn=0.1)
+    du = nu.float() * kw["c_out"] + xx * kw["c_skip"]
+    dc = nc.float() * kw["c_out"] + xx * kw["c_skip"]
+    den = du + kw["cfg"] * (dc - du)
+    xo, do = ops.sampler_update(xx, nu, nc, old, eps, mode=1, **kw)
+    report("sampler_update mode1 x", xo, kw["m1"] * xx - kw["m2"] * (kw["m3"] * den - kw["m4"] * old) + kw["mn"] * eps)
+    report("sampler_update den", do, den)
+    xo, _ = ops.sampler_update(xx, nu, nc, None, eps, mode=0, **kw)
+    report("sampler_update mode0 x", xo, kw["m1"] * xx - kw["m2"] * den + kw["mn"] * eps)
+    xo, _ = ops.sampler_update(xx, nu, nc, None, None, mode=2, **kw)
+    report("sampler_update mode2 x", xo, den)
+
+
+if __name__ == "__main__":
+    cases = sys.argv[1:] or ["all"]
+    print("device:", torch.cuda.get_device_name(0), "SMs:", ops.device_check(), flush=True)
+    for c in cases:
+        print(f"[{c}]", flush=True)
+        if c in ("gemm", "all"):
+            probe_gemm()
+        if c in ("attn0", "all"):
+            probe_attn(0)
+        if c in ("attn1", "all"):
+            probe_attn(1)
+        if c in ("rows", "all"):
+            probe_rows()
