@@ -1,0 +1,326 @@
+"""bench.py — seconds per 49-frame 480x720 50-step CFG denoise (BASELINE.json metric), one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            ours: hand-written sm_100a kernels via the C-ABI
+  python bench.py --impl reference [--gpus N --steps K --warmup W] the reference's CPU path (oracle port) on host cores
+
+A "step" is ONE sampler step of the job: a CFG network evaluation (15-layer control DiT + 30-layer main DiT, batch
+[uncond, cond], N = 17 776 tokens) plus the fused denoiser-scale + CFG + DPM++(2M) SDE update.  50 steps = one video,
+so value = 50 x (timed seconds / K).  N = 1: both CFG rows on one GPU (BASELINE configs[1]); N = 2: CFG-parallel;
+N = 4 / 8: CFG x ring sequence parallel (2 / 4).  Synthetic latents / text features / semantic features of the named
+shapes, seeded random-init weights of the named architecture (no checkpoints exist offline).
+
+Timing: W >= 3 untimed warm-up steps; K timed steps bracketed by barrier + cuda synchronize, CUDA events on the
+launch stream, max over ranks.  The working set of one step (5.3 GB of weights + ~1.5 GB of activations per
+layer) is far larger than the 126 MB L2, so no explicit flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "seconds per 49-frame 480x720 50-step CFG denoise"
+UNIT = "s"
+SAMPLER_STEPS = 50
+# algorithmic FLOPs: 2MNK per GEMM + 4 N^2 d per attention layer-sample
+FLOP_PER_CFG_STEP_FULL = 3.6393e14
+FLOP_PER_CFG_STEP_CONFIG1 = 7.793e12
+
+
+def peaks():
+    try:
+        p = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch.distributed as dist
+
+    from landiff_b200 import _C, dit, ops, parallel
+    from landiff_b200.factory import FULL, build_warp, random_init_
+    from landiff_b200.sampling import VPSDEDPMPP2MSampler
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ops.device_check()
+    layout = parallel.make_layout(world, rank)
+    sp_group = None
+    if world > 1:
+        sp_group, _ = parallel.new_subgroups(layout)
+
+    cfg = FULL
+    warp = build_warp(cfg, device=dev)
+    random_init_(warp, seed=0)
+    parallel.attach(warp, layout, sp_group, dev)
+    cfg_group = parallel.CFGGroup(layout) if world > 1 else None
+    sampler = VPSDEDPMPP2MSampler(num_steps=SAMPLER_STEPS, device="cuda")
+
+    g = torch.Generator().manual_seed(1)
+    x_host = torch.randn(1, cfg.latent_t, cfg.in_channels, cfg.latent_h, cfg.latent_w, generator=g).pin_memory()
+    ctx_host = (torch.randn(1, cfg.text_length, cfg.text_hidden, generator=g) * 0.2).to(torch.bfloat16).pin_memory()
+    sem_host = (torch.randn(1, cfg.latent_t, cfg.in_channels, cfg.latent_h, cfg.latent_w, generator=g) * 0.1).to(torch.bfloat16)
+    dit.InferValueRegistry.clear()
+    dit.InferValueRegistry.register("semantic_feature", sem_host.to(dev))
+    cond = {"crossattn": ctx_host.to(dev)}
+    uc = {"crossattn": torch.zeros_like(cond["crossattn"])}
+    torch.manual_seed(42)  # sampler noise stream, identical on every rank
+
+    # attention-kernel timing hook (the dominant kernel): CUDA events on the launch stream around each launch
+    attn_events = []
+    orig_attention = ops.attention
+
+    def timed_attention(*a, **k):
+        if not timed_attention.on:
+            return orig_attention(*a, **k)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig_attention(*a, **k)
+        e.record()
+        attn_events.append((s, e))
+        return r
+
+    timed_attention.on = False
+    ops.attention = timed_attention
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def sample_k(x0, k, start=0):
+        """k consecutive sampler steps of the 50-step schedule (wrapping around for k > 50)."""
+        x, done = x0, 0
+        while done < k:
+            chunk = min(SAMPLER_STEPS - start, k - done)
+            x = sampler.sample(warp, x, cond, uc, cfg_group=cfg_group, start_step=start, max_steps=chunk)
+            done += chunk
+            start = 0
+        return x
+
+    x_dev = x_host.to(dev, non_blocking=True)
+    barrier()
+    sample_k(x_dev, max(args.warmup, 3))
+    barrier()
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = _C.LAUNCHES[0]
+    timed_attention.on = True
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    sample_k(x_dev, args.steps)
+    ev1.record()
+    barrier()
+    timed_attention.on = False
+    ms = ev0.elapsed_time(ev1)
+    launches = _C.LAUNCHES[0] - launches0
+    clk = clocks.stop() if rank == 0 else None
+    attn_ms = [s.elapsed_time(e) for s, e in attn_events]
+
+    # e2e: same steps through the public API with HOST buffers: per step H2D of the step's inputs (latent x from pinned
+    # memory, text features) and D2H of the step's result (the updated latent)
+    x_out_host = torch.empty_like(x_host).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = min(args.steps, 10)
+    e0.record()
+    for i in range(e2e_steps):
+        xd = x_host.to(dev, non_blocking=True)
+        cd = {"crossattn": ctx_host.to(dev, non_blocking=True)}
+        xo = sampler.sample(warp, xd, cd, uc, cfg_group=cfg_group, start_step=i % SAMPLER_STEPS, max_steps=1)
+        x_out_host.copy_(xo, non_blocking=True)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        ms_per_step = ms / args.steps
+        value = ms_per_step * SAMPLER_STEPS / 1e3
+        tf_peak, bw_peak, how = peaks()
+        # dominant kernel: attention.  algorithmic FLOPs per launch = 4 * nq * nkv * 64 * (B*H) for this rank's launch
+        b_rows = 2 if layout.cfg_size == 1 else 1
+        nq = cfg.n_tok // layout.sp_size
+        flop_per_launch = 4.0 * nq * nq * 64 * b_rows * cfg.num_heads
+        attn_avg = sum(attn_ms) / max(len(attn_ms), 1)
+        achieved = flop_per_launch / (attn_avg * 1e-3) / 1e12 if attn_avg > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 3), "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "LanDiff ControlDiffWarp (15-layer control + 30-layer main DiT, d=1920, 30 heads) "
+                                   "49-frame 480x720 latent 13x16x60x90, 17776 tokens, CFG batch 2, DPM++2M SDE, "
+                                   "value = 50 x per-step time",
+                       "parallelism": {1: "single GPU", 2: "cfg2", 4: "cfg2 x ring-sp2", 8: "cfg2 x ring-sp4"}.get(world, f"cfg{layout.cfg_size} x sp{layout.sp_size}"),
+                       "l2": "per-step working set (>6 GB) exceeds the 126 MB L2; no explicit flush",
+                       "weights": "seeded random init N(0, 0.02^2)", "sampler_steps_per_video": SAMPLER_STEPS},
+            "tensor_frac_of_peak_whole_step": round(FLOP_PER_CFG_STEP_FULL / (ms_per_step * 1e-3) / world / 1e12 / tf_peak, 4),
+            "roofline": {"bound": "tensor", "kernel": "attn_kernel (tcgen05 flash attention, head_dim 64)",
+                         "achieved": round(achieved, 1), "peak": tf_peak, "unit": "TFLOP/s",
+                         "frac": round(achieved / tf_peak, 4), "traffic": None, "peak_source": how,
+                         "launch_ms": round(attn_avg, 4), "launches_timed": len(attn_ms),
+                         "share_of_step": round(sum(attn_ms) / ms, 4) if ms > 0 else None},
+            "e2e": {"value": round(e2e_ms * SAMPLER_STEPS / 1e3, 4), "unit": UNIT,
+                    "h2d_bytes_per_step": x_host.numel() * 4 + ctx_host.numel() * 2,
+                    "d2h_bytes_per_step": x_host.numel() * 4, "steps_timed": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": clk,
+        }
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline_sample(max_seconds=40)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------- CPU side
+def cpu_baseline_sample(max_seconds=40, layers=None):
+    """The oracle port (plain PyTorch fp32, the reference module graph restated) on the host cores: one CFG step at
+    BASELINE config 1 (5 frames 240x352, N = 886 tokens), extrapolated to the full job by algorithmic FLOPs."""
+    import dataclasses
+
+    from oracle import dit_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.CONFIG1
+    frac = 1.0
+    if layers is not None:
+        cfg = dataclasses.replace(cfg, main_layers=layers[0], control_layers=layers[1])
+        frac = (layers[0] + layers[1] * 1.033) / (30 + 15 * 1.033)
+    sdc = O.cast_state_dict(O.random_state_dict(cfg, True, seed=10), torch.float32)
+    sdm = O.cast_state_dict(O.random_state_dict(cfg, False, seed=11), torch.float32)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, cfg.latent_t, 16, cfg.latent_h, cfg.latent_w, generator=g)
+    ctx = torch.randn(2, cfg.text_length, cfg.text_hidden, generator=g) * 0.2
+    sem = torch.randn(1, cfg.latent_t, 16, cfg.latent_h, cfg.latent_w, generator=g) * 0.1
+    t = torch.tensor([519.0, 519.0])
+    t0 = time.perf_counter()
+    O.warp_forward(sdc, sdm, cfg, x, t, ctx, sem)
+    dt = time.perf_counter() - t0
+    flop = FLOP_PER_CFG_STEP_CONFIG1 * frac
+    full_job = dt * (FLOP_PER_CFG_STEP_FULL / flop) * SAMPLER_STEPS
+    return {"value": round(full_job, 1), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"one CFG step (batch 2) of the oracle port at BASELINE config 1 (N=886 tokens, "
+                      f"{cfg.main_layers}+{cfg.control_layers} layers, fp32) took {dt:.2f} s on {cores} threads; "
+                      f"extrapolated to 50 full-shape steps by algorithmic FLOPs (x{FLOP_PER_CFG_STEP_FULL / flop:.1f} x 50)",
+            "sample_seconds": round(dt, 3), "sample_tflops": round(flop / dt / 1e12, 3)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself needs the
+    un-vendored SwissArmyTransformer and cannot be installed offline).  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total = max(args.warmup, 0) + args.steps
+    layers = None if total <= 6 else ((6, 3) if total <= 30 else (2, 1))  # keep the whole run within a few minutes
+    vals = []
+    for i in range(total):
+        r = cpu_baseline_sample(layers=layers)
+        if i >= args.warmup:
+            vals.append(r)
+    value = sum(v["value"] for v in vals) / len(vals)
+    last = vals[-1]
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(value / SAMPLER_STEPS * 1e3, 1),
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "same job as the default arm; each step = one bounded sample (see cpu_baseline.sample), "
+                                   "extrapolated by algorithmic FLOPs"},
+            "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": last["cores"], "kind": "port",
+                             "sample": last["sample"]},
+            "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,25 @@ __device__ __forceinline__ void store8_bf16(bf16* p, const float* f) {
   *reinterpret_cast<uint4*>(p) = v;
 }
 
+// residual stream may be kept in fp32 (main net) or bf16 (control net): element-index based typed access
+__device__ __forceinline__ void load8_stream(const void* base, bool is_f32, int64_t idx, float* f) {
+  if (is_f32) {
+    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    load8_bf16(reinterpret_cast<const bf16*>(base) + idx, f);
+  }
+}
+__device__ __forceinline__ void store8_stream(void* base, bool is_f32, int64_t idx, const float* f) {
+  if (is_f32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    store8_bf16(reinterpret_cast<bf16*>(base) + idx, f);
+  }
+}
+
 // ---- epilogues on a 32-column chunk held by one thread (one output row) -------------------------------------
 template <int EPI>
 __device__ __forceinline__ void epilogue32(const ld_gemm_args& p, const RowCtx& rc, int col, const uint32_t* r) {
@@ -83,13 +102,13 @@ __device__ __forceinline__ void epilogue32(const ld_gemm_args& p, const RowCtx& 
     for (int g = 0; g < 4; ++g) store8_bf16(o + g * 8, acc + g * 8);
   } else if constexpr (EPI == LD_EPI_GATED_RESID) {
     const float* gate = (rc.is_text ? p.gate_txt : p.gate_img) + (int64_t)rc.b * p.mod_batch_stride + col;
-    const bf16* res = reinterpret_cast<const bf16*>(p.resid) + rc.out_row * p.ld_out + col;
-    const bf16* add2 = p.add2 ? reinterpret_cast<const bf16*>(p.add2) + rc.out_row * p.ld_out + col : nullptr;
-    bf16* o = reinterpret_cast<bf16*>(p.out) + rc.out_row * p.ld_out + col;
+    const int64_t eidx = rc.out_row * p.ld_out + col;
+    const bf16* add2 = p.add2 ? reinterpret_cast<const bf16*>(p.add2) + eidx : nullptr;
+    const bool rf32 = p.resid_f32 != 0, of32 = p.out_f32 != 0;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float rv[8];
-      load8_bf16(res + g * 8, rv);
+      load8_stream(p.resid, rf32, eidx + g * 8, rv);
       const float4 g0 = *reinterpret_cast<const float4*>(gate + g * 8);
       const float4 g1 = *reinterpret_cast<const float4*>(gate + g * 8 + 4);
       const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -102,11 +121,12 @@ __device__ __forceinline__ void epilogue32(const ld_gemm_args& p, const RowCtx& 
 #pragma unroll
         for (int i = 0; i < 8; ++i) ov[i] += av[i];
       }
-      store8_bf16(o + g * 8, ov);
+      store8_stream(p.out, of32, eidx + g * 8, ov);
     }
   } else if constexpr (EPI == LD_EPI_BIAS_POS) {
     const bf16* pos = reinterpret_cast<const bf16*>(p.pos) + (int64_t)(p.tok_offset + rc.t) * p.N + col;
-    bf16* o = reinterpret_cast<bf16*>(p.out) + rc.out_row * p.ld_out + col;
+    const int64_t eidx = rc.out_row * p.ld_out + col;
+    const bool of32 = p.out_f32 != 0;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float pv[8];
@@ -114,7 +134,7 @@ __device__ __forceinline__ void epilogue32(const ld_gemm_args& p, const RowCtx& 
       float ov[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) ov[i] = acc[g * 8 + i] + pv[i];
-      store8_bf16(o + g * 8, ov);
+      store8_stream(p.out, of32, eidx + g * 8, ov);
     }
   } else if constexpr (EPI == LD_EPI_UNPATCHIFY) {
     // col = c*4 + pp*2 + qq  ->  out[b, t, c, 2h+pp, 2w+qq]      (dit_video_concat.py:392-410)

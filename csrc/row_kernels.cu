@@ -28,6 +28,19 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   return v;
 }
 
+// load one 8-element vector of a row stored as bf16 or fp32
+template <typename TX>
+__device__ __forceinline__ void load_row_vec(const TX* row, int v, float* f);
+template <>
+__device__ __forceinline__ void load_row_vec<bf16>(const bf16* row, int v, float* f) {
+  unpack8(reinterpret_cast<const uint4*>(row)[v], f);
+}
+template <>
+__device__ __forceinline__ void load_row_vec<float>(const float* row, int v, float* f) {
+  const float4 a = reinterpret_cast<const float4*>(row)[2 * v], b = reinterpret_cast<const float4*>(row)[2 * v + 1];
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
 // LayerNorm statistics of a row held as vals[kMaxVec][8] (lanes own vectors lane, lane+32, ...).
 __device__ __forceinline__ void row_stats(const float (*vals)[8], int nvec, int lane, int D, float eps, float& mean,
                                           float& rstd) {
@@ -53,7 +66,8 @@ __device__ __forceinline__ void row_stats(const float (*vals)[8], int nvec, int 
 }
 
 // out = LN(x) * (1 + scale[seg]) + shift[seg]
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict__ x, bf16* __restrict__ out,
+template <typename TX>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const TX* __restrict__ x, bf16* __restrict__ out,
                                                           const bf16* __restrict__ w, const bf16* __restrict__ b,
                                                           float eps, const float* __restrict__ shift_img,
                                                           const float* __restrict__ scale_img,
@@ -70,11 +84,11 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
     const bool is_text = (tok_offset + t) < text_len;
     const float* shift = (is_text ? shift_txt : shift_img) + (int64_t)bidx * mod_stride;
     const float* scale = (is_text ? scale_txt : scale_img) + (int64_t)bidx * mod_stride;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * D);
+    const TX* xr = x + (int64_t)row * D;
     float vals[kMaxVec][8];
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i)
-      if (lane + 32 * i < nvec) unpack8(xr[lane + 32 * i], vals[i]);
+      if (lane + 32 * i < nvec) load_row_vec<TX>(xr, lane + 32 * i, vals[i]);
     float mean, rstd;
     row_stats(vals, nvec, lane, D, eps, mean, rstd);
     uint4* orow = reinterpret_cast<uint4*>(out + (int64_t)row * D);
@@ -101,7 +115,8 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
 }
 
 // y = LN2(LN1(x_img)) * (1 + scale) + shift ; only image rows are produced (compacted)
-__global__ void __launch_bounds__(256) final_norm_kernel(const bf16* __restrict__ x, bf16* __restrict__ out,
+template <typename TX>
+__global__ void __launch_bounds__(256) final_norm_kernel(const TX* __restrict__ x, bf16* __restrict__ out,
                                                          const bf16* __restrict__ w1, const bf16* __restrict__ b1,
                                                          float eps1, const bf16* __restrict__ w2,
                                                          const bf16* __restrict__ b2, float eps2,
@@ -117,11 +132,11 @@ __global__ void __launch_bounds__(256) final_norm_kernel(const bf16* __restrict_
     const int bidx = orow_i / n_img;
     const int g = orow_i - bidx * n_img;
     const int64_t in_row = (int64_t)bidx * rows_per_batch + first_img + g;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + in_row * D);
+    const TX* xr = x + in_row * D;
     float vals[kMaxVec][8];
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i)
-      if (lane + 32 * i < nvec) unpack8(xr[lane + 32 * i], vals[i]);
+      if (lane + 32 * i < nvec) load_row_vec<TX>(xr, lane + 32 * i, vals[i]);
     float mean, rstd;
     row_stats(vals, nvec, lane, D, eps1, mean, rstd);
 #pragma unroll
@@ -261,8 +276,9 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
   if ((dim & 1) && k == 0) out[(int64_t)b * dim + dim - 1] = 0.f;
 }
 
-__global__ void __launch_bounds__(256) sampler_update_kernel(const float* __restrict__ x, const bf16* __restrict__ net_u,
-                                                             const bf16* __restrict__ net_c,
+template <typename TN>
+__global__ void __launch_bounds__(256) sampler_update_kernel(const float* __restrict__ x, const TN* __restrict__ net_u,
+                                                             const TN* __restrict__ net_c,
                                                              const float* __restrict__ old_den,
                                                              const float* __restrict__ eps, float* __restrict__ x_out,
                                                              float* __restrict__ den_out, int64_t n, float c_skip,
@@ -271,8 +287,8 @@ __global__ void __launch_bounds__(256) sampler_update_kernel(const float* __rest
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float xv = x[i];
     // same operation order as the reference: net*c_out + x*c_skip (fp32), then x_u + s*(x_c - x_u)
-    const float du = __bfloat162float(net_u[i]) * c_out + xv * c_skip;
-    const float dc = __bfloat162float(net_c[i]) * c_out + xv * c_skip;
+    const float du = (float)net_u[i] * c_out + xv * c_skip;
+    const float dc = (float)net_c[i] * c_out + xv * c_skip;
     const float den = du + cfg * (dc - du);
     float xo;
     if (mode == 2) {
@@ -299,7 +315,7 @@ static inline int grid_for(int64_t work_items, int per_block, int max_blocks) {
 
 using namespace ld;
 
-extern "C" int ld_layernorm_modulate(const void* x, void* out, const void* w, const void* b, float eps,
+extern "C" int ld_layernorm_modulate(const void* x, int x_is_f32, void* out, const void* w, const void* b, float eps,
                                      const float* shift_img, const float* scale_img, const float* shift_txt,
                                      const float* scale_txt, int64_t mod_batch_stride, int batch, int rows_per_batch,
                                      int tok_offset, int text_len, int D, void* stream) {
@@ -310,15 +326,21 @@ extern "C" int ld_layernorm_modulate(const void* x, void* out, const void* w, co
   LD_CHECK_ARG(batch > 0 && rows_per_batch > 0, "ld_layernorm_modulate: empty input");
   const int rows = batch * rows_per_batch;
   const int grid = grid_for(rows, 8, sm_count() * 16);
-  ln_modulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, (const bf16*)w, (const bf16*)b, eps,
-                                                              shift_img, scale_img, shift_txt, scale_txt,
-                                                              mod_batch_stride, rows, rows_per_batch, tok_offset,
-                                                              text_len, D);
+  if (x_is_f32)
+    ln_modulate_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
+                                                                       eps, shift_img, scale_img, shift_txt, scale_txt,
+                                                                       mod_batch_stride, rows, rows_per_batch, tok_offset,
+                                                                       text_len, D);
+  else
+    ln_modulate_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
+                                                                      eps, shift_img, scale_img, shift_txt, scale_txt,
+                                                                      mod_batch_stride, rows, rows_per_batch, tok_offset,
+                                                                      text_len, D);
   LD_CHECK_CUDA(cudaGetLastError());
   return LD_OK;
 }
 
-extern "C" int ld_final_norm_modulate(const void* x, void* out, const void* w1, const void* b1, float eps1,
+extern "C" int ld_final_norm_modulate(const void* x, int x_is_f32, void* out, const void* w1, const void* b1, float eps1,
                                       const void* w2, const void* b2, float eps2, const float* shift,
                                       const float* scale, int64_t mod_batch_stride, int batch, int rows_per_batch,
                                       int tok_offset, int text_len, int D, void* stream) {
@@ -331,9 +353,14 @@ extern "C" int ld_final_norm_modulate(const void* x, void* out, const void* w1, 
   LD_CHECK_ARG(first_img < rows_per_batch, "ld_final_norm_modulate: shard holds no image rows");
   const int rows = batch * (rows_per_batch - first_img);
   const int grid = grid_for(rows, 8, sm_count() * 16);
-  final_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, (const bf16*)w1, (const bf16*)b1, eps1,
-                                                             (const bf16*)w2, (const bf16*)b2, eps2, shift, scale,
-                                                             mod_batch_stride, batch, rows_per_batch, first_img, D);
+  if (x_is_f32)
+    final_norm_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (bf16*)out, (const bf16*)w1, (const bf16*)b1,
+                                                                      eps1, (const bf16*)w2, (const bf16*)b2, eps2, shift, scale,
+                                                                      mod_batch_stride, batch, rows_per_batch, first_img, D);
+  else
+    final_norm_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, (const bf16*)w1, (const bf16*)b1,
+                                                                     eps1, (const bf16*)w2, (const bf16*)b2, eps2, shift, scale,
+                                                                     mod_batch_stride, batch, rows_per_batch, first_img, D);
   LD_CHECK_CUDA(cudaGetLastError());
   return LD_OK;
 }
@@ -392,7 +419,8 @@ extern "C" int ld_timestep_embedding(const float* t, float* out, int batch, int 
 
 extern "C" int ld_sampler_update(const float* x, const void* net_u, const void* net_c, const float* old_den,
                                  const float* eps, float* x_out, float* den_out, int64_t n, float c_skip, float c_out,
-                                 float cfg, float m1, float m2, float m3, float m4, float mn, int mode, void* stream) {
+                                 float cfg, float m1, float m2, float m3, float m4, float mn, int mode, int net_is_f32,
+                                 void* stream) {
   int rc = check_device();
   if (rc != LD_OK) return rc;
   LD_CHECK_ARG(x && net_u && net_c && x_out && den_out && n > 0, "ld_sampler_update: null pointer / empty");
@@ -400,8 +428,14 @@ extern "C" int ld_sampler_update(const float* x, const void* net_u, const void* 
   LD_CHECK_ARG(mode == 2 || eps != nullptr, "ld_sampler_update: eps required");
   LD_CHECK_ARG(mode != 1 || old_den != nullptr, "ld_sampler_update: old_den required for mode 1");
   const int grid = grid_for(n, 256, sm_count() * 8);
-  sampler_update_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)net_u, (const bf16*)net_c, old_den, eps, x_out,
-                                                                 den_out, n, c_skip, c_out, cfg, m1, m2, m3, m4, mn, mode);
+  if (net_is_f32)
+    sampler_update_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const float*)net_u, (const float*)net_c, old_den, eps,
+                                                                          x_out, den_out, n, c_skip, c_out, cfg, m1, m2, m3, m4,
+                                                                          mn, mode);
+  else
+    sampler_update_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)net_u, (const bf16*)net_c, old_den, eps,
+                                                                         x_out, den_out, n, c_skip, c_out, cfg, m1, m2, m3, m4,
+                                                                         mn, mode);
   LD_CHECK_CUDA(cudaGetLastError());
   return LD_OK;
 }

@@ -73,6 +73,9 @@ typedef struct ld_gemm_args {
   const void* pos;
   /* UNPATCHIFY: out is bf16 [B, T, C, 2*Hp, 2*Wp]; image token index g = tok_offset + t - text_len */
   int32_t T, Hp, Wp, C;
+  /* residual-stream dtype (GATED_RESID: resid/out, BIAS_POS: out): 0 = bf16 (the reference's rounding points),
+     1 = fp32 (the main net keeps its 30-layer residual stream in fp32; add2 stays bf16) */
+  int32_t resid_f32, out_f32;
 } ld_gemm_args;
 
 int ld_gemm_bf16(const ld_gemm_args* args, void* stream);
@@ -93,16 +96,17 @@ int ld_attention_merge(float* o_acc, float* lse_acc, const float* o_new, const f
 
 /* ---- fused memory-bound row kernels ------------------------------------------------------------------- */
 /* out = LayerNorm(x; w, b, eps) * (1 + scale[seg]) + shift[seg]   (dit_video_concat.py:577-586, 601-611, :388)
-   x,out: bf16 [B*rows_per_batch, D]; w,b: bf16 [D]; shift_x / scale_x: fp32 [D] of sample 0. D % 8 == 0, D <= 2048 */
-int ld_layernorm_modulate(const void* x, void* out, const void* w, const void* b, float eps,
+   x: bf16 or fp32 (x_is_f32) [B*rows_per_batch, D]; out: bf16; w,b: bf16 [D]; shift_x / scale_x: fp32 [D] of sample 0.
+   D % 8 == 0, D <= 2048 */
+int ld_layernorm_modulate(const void* x, int x_is_f32, void* out, const void* w, const void* b, float eps,
                           const float* shift_img, const float* scale_img, const float* shift_txt,
                           const float* scale_txt, int64_t mod_batch_stride, int batch, int rows_per_batch,
                           int tok_offset, int text_len, int D, void* stream);
 
 /* final layer front half: y = LN2(LN1(x[image rows]); eps2) * (1 + scale) + shift  -> bf16 [B*n_img, D]
    (SAT final_layernorm + FinalLayerMixin.final_forward, dit_video_concat.py:442-452).  x: [B, rows_per_batch, D];
-   image rows are those with tok_offset + t >= text_len. */
-int ld_final_norm_modulate(const void* x, void* out, const void* w1, const void* b1, float eps1, const void* w2,
+   image rows are those with tok_offset + t >= text_len.  x is bf16 or fp32 (x_is_f32). */
+int ld_final_norm_modulate(const void* x, int x_is_f32, void* out, const void* w1, const void* b1, float eps1, const void* w2,
                            const void* b2, float eps2, const float* shift, const float* scale,
                            int64_t mod_batch_stride, int batch, int rows_per_batch, int tok_offset, int text_len,
                            int D, void* stream);
@@ -128,10 +132,12 @@ int ld_timestep_embedding(const float* t, float* out, int batch, int dim, float 
      mode 0 (first step):  x' = m1*x - m2*den + mn*eps                        (sampling.py:771-774)
      mode 1 (middle):      x' = m1*x - m2*(m3*den - m4*old) + mn*eps          (sampling.py:776-781)
      mode 2 (last):        x' = den                                           (sampling.py:750-751)
-   net_u/net_c: bf16 network outputs; x, old, eps, x_out, den_out: fp32. */
+   net_u/net_c: bf16 network outputs (net_is_f32 = 0) or fp32 rows (net_is_f32 = 1, e.g. already-denoised rows with
+   c_skip = 0, c_out = 1 when the reference DiscreteDenoiser stays in the loop); x, old, eps, x_out, den_out: fp32. */
 int ld_sampler_update(const float* x, const void* net_u, const void* net_c, const float* old_den,
                       const float* eps, float* x_out, float* den_out, int64_t n, float c_skip, float c_out,
-                      float cfg, float m1, float m2, float m3, float m4, float mn, int mode, void* stream);
+                      float cfg, float m1, float m2, float m3, float m4, float mn, int mode, int net_is_f32,
+                      void* stream);
 
 #ifdef __cplusplus
 }

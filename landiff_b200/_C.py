@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("heads", C.c_int32), ("qkv_rows", C.c_int32), ("qkv_row_offset", C.c_int32),
         ("pos", C.c_void_p),
         ("T", C.c_int32), ("Hp", C.c_int32), ("Wp", C.c_int32), ("C", C.c_int32),
+        ("resid_f32", C.c_int32), ("out_f32", C.c_int32),
     ]
 
 
@@ -45,12 +46,12 @@ SIGNATURES = {
     "ld_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "ld_attention_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ld_attention_merge": (C.c_int, [_fp, _fp, _fp, _fp, _vp, _i, _i, _i, _vp]),
-    "ld_layernorm_modulate": (C.c_int, [_vp, _vp, _vp, _vp, _f, _fp, _fp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),
-    "ld_final_norm_modulate": (C.c_int, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _f, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "ld_layernorm_modulate": (C.c_int, [_vp, _i, _vp, _vp, _vp, _f, _fp, _fp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "ld_final_norm_modulate": (C.c_int, [_vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),
     "ld_patchify": (C.c_int, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ld_small_linear": (C.c_int, [_fp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
     "ld_timestep_embedding": (C.c_int, [_fp, _fp, _i, _i, _f, _i, _vp]),
-    "ld_sampler_update": (C.c_int, [_fp, _vp, _vp, _fp, _fp, _fp, _fp, _i64] + [_f] * 8 + [_i, _vp]),
+    "ld_sampler_update": (C.c_int, [_fp, _vp, _vp, _fp, _fp, _fp, _fp, _i64] + [_f] * 8 + [_i, _i, _vp]),
 }
 
 _lib = None
@@ -81,7 +82,12 @@ class LanDiffB200Error(RuntimeError):
     pass
 
 
+LAUNCHES = [0]  # kernels launched through the C-ABI (every compute entry point launches exactly one kernel)
+
+
 def check(rc: int, what: str) -> None:
+    if rc == LD_OK and what != "ld_device_check":
+        LAUNCHES[0] += 1
     if rc != LD_OK:
         msg = load().ld_last_error().decode(errors="replace")
         raise LanDiffB200Error(f"{what} failed (code {rc}): {msg}")

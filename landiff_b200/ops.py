@@ -94,14 +94,21 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epilogue: int, bias: Optional[torc
         else:
             if out is None:
                 out = torch.empty((M, N), dtype=BF16, device=a.device)
-            _chk(out, BF16, "out", contiguous=False)
+            if out.dtype == F32 and epilogue in (EPI_GATED_RESID, EPI_BIAS_POS):
+                g.out_f32 = 1  # fp32 residual stream
+            else:
+                _chk(out, BF16, "out", contiguous=False)
+            if not out.is_cuda:
+                raise ValueError("out must be a CUDA tensor")
             if out.stride(-1) != 1:
                 raise ValueError("gemm: out must have unit inner stride")
             g.ld_out = out.stride(0) if out.dim() == 2 else N
         g.out = out.data_ptr()
         ret = out
         if epilogue == EPI_GATED_RESID:
-            _chk(resid, BF16, "resid", contiguous=False)
+            if resid.dtype == F32:
+                g.resid_f32 = 1
+            _chk(resid, resid.dtype if resid.dtype in (BF16, F32) else BF16, "resid", contiguous=False)
             _chk(gate_img, F32, "gate_img", contiguous=False)
             _chk(gate_txt, F32, "gate_txt", contiguous=False)
             g.resid, g.gate_img, g.gate_txt = resid.data_ptr(), gate_img.data_ptr(), gate_txt.data_ptr()
@@ -149,13 +156,14 @@ def attention_merge(o_acc, lse_acc, o_new, lse_new, out_bf16, batch, heads, nq) 
 
 def layernorm_modulate(x, w, b, eps, shift_img, scale_img, shift_txt, scale_txt, mod_batch_stride, batch,
                        rows_per_batch, tok_offset, text_len, out=None):
-    _chk(x, BF16, "x")
+    _chk(x, x.dtype if x.dtype in (BF16, F32) else BF16, "x")
     D = x.shape[-1]
     if out is None:
-        out = torch.empty_like(x)
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    _chk(out, BF16, "out")
     for t_ in (shift_img, scale_img, shift_txt, scale_txt):
         _chk(t_, F32, "modulation", contiguous=False)
-    check(_C.load().ld_layernorm_modulate(x.data_ptr(), out.data_ptr(), w.data_ptr(), b.data_ptr(), eps,
+    check(_C.load().ld_layernorm_modulate(x.data_ptr(), int(x.dtype == F32), out.data_ptr(), w.data_ptr(), b.data_ptr(), eps,
                                           shift_img.data_ptr(), scale_img.data_ptr(), shift_txt.data_ptr(),
                                           scale_txt.data_ptr(), mod_batch_stride, batch, rows_per_batch, tok_offset,
                                           text_len, D, _stream()), "ld_layernorm_modulate")
@@ -164,13 +172,13 @@ def layernorm_modulate(x, w, b, eps, shift_img, scale_img, shift_txt, scale_txt,
 
 def final_norm_modulate(x, w1, b1, eps1, w2, b2, eps2, shift, scale, mod_batch_stride, batch, rows_per_batch,
                         tok_offset, text_len, out=None):
-    _chk(x, BF16, "x")
+    _chk(x, x.dtype if x.dtype in (BF16, F32) else BF16, "x")
     D = x.shape[-1]
     first_img = max(text_len - tok_offset, 0)
     n_img = rows_per_batch - first_img
     if out is None:
         out = torch.empty((batch * n_img, D), dtype=BF16, device=x.device)
-    check(_C.load().ld_final_norm_modulate(x.data_ptr(), out.data_ptr(), w1.data_ptr(), b1.data_ptr(), eps1,
+    check(_C.load().ld_final_norm_modulate(x.data_ptr(), int(x.dtype == F32), out.data_ptr(), w1.data_ptr(), b1.data_ptr(), eps1,
                                            w2.data_ptr(), b2.data_ptr(), eps2, shift.data_ptr(), scale.data_ptr(),
                                            mod_batch_stride, batch, rows_per_batch, tok_offset, text_len, D, _stream()),
           "ld_final_norm_modulate")
@@ -222,10 +230,17 @@ def timestep_embedding(t, dim, max_period=10000.0, round_bf16=True, out=None):
 
 
 def sampler_update(x, net_u, net_c, old_den, eps, *, c_skip, c_out, cfg, m1=0.0, m2=0.0, m3=0.0, m4=0.0, mn=0.0, mode=0,
-                   x_out=None, den_out=None):
+                   x_out=None, den_out=None, net_dtype=BF16):
     _chk(x, F32, "x")
-    _chk(net_u, BF16, "net_u")
-    _chk(net_c, BF16, "net_c")
+    _chk(net_u, net_dtype, "net_u")
+    _chk(net_c, net_dtype, "net_c")
+    if net_u.numel() != x.numel() or net_c.numel() != x.numel():
+        raise ValueError("sampler_update: net_u/net_c must have x's element count")
+    for nm, t_ in (("old_den", old_den), ("eps", eps)):
+        if t_ is not None:
+            _chk(t_, F32, nm)
+            if t_.numel() != x.numel():
+                raise ValueError(f"sampler_update: {nm} size")
     n = x.numel()
     if x_out is None:
         x_out = torch.empty_like(x)
@@ -237,8 +252,15 @@ def sampler_update(x, net_u, net_c, old_den, eps, *, c_skip, c_out, cfg, m1=0.0,
 
     check(_C.load().ld_sampler_update(x.data_ptr(), net_u.data_ptr(), net_c.data_ptr(), _ptr(old_den), _ptr(eps),
                                       x_out.data_ptr(), den_out.data_ptr(), n, fin(c_skip), fin(c_out), fin(cfg), fin(m1),
-                                      fin(m2), fin(m3), fin(m4), fin(mn), mode, _stream()), "ld_sampler_update")
+                                      fin(m2), fin(m3), fin(m4), fin(mn), mode, int(net_dtype == F32), _stream()),
+          "ld_sampler_update")
     return x_out, den_out
+
+
+def sampler_update_f32(x, den_u, den_c, old_den, eps, *, cfg, m1=0.0, m2=0.0, m3=0.0, m4=0.0, mn=0.0, mode=0):
+    """CFG combine + DPM++ update on already-denoised fp32 rows (reference DiscreteDenoiser kept in the loop)."""
+    return sampler_update(x, den_u, den_c, old_den, eps, c_skip=0.0, c_out=1.0, cfg=cfg, m1=m1, m2=m2, m3=m3, m4=m4, mn=mn,
+                          mode=mode, net_dtype=F32)
 
 
 _registered = False

@@ -82,28 +82,35 @@ def _params(cfg: DiTConfig, layers: int, control: bool):
     return p
 
 
-def seeded_init_(module: torch.nn.Module, seed: int) -> None:
-    """every weight N(0,0.02^2), biases N(0,0.02^2), LayerNorm weight 1+N(0,0.02^2); zero-init tensors
-    (zero_linears) are re-randomised too so the control path carries signal; pos_embedding is left as built."""
+def seeded_init_(module: torch.nn.Module, seed: int, strong: bool = False) -> None:
+    """SURVEY §8d init: every weight N(0,0.02^2), biases N(0,0.02^2), LayerNorm weight 1+N(0,0.02^2); zero-init tensors
+    (zero_linears) are re-randomised too so the control path carries signal; pos_embedding is left as built.
+    `strong=True` is the structural-test init: matrices N(0, 1/fan_in), biases / norm offsets N(0, 0.1^2), so that the
+    time embedding, every adaLN shift/scale/gate and the control branch are O(1) and a mis-ordered chunk or a wrong
+    segment shows up as an O(1) error instead of hiding under the tolerance."""
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for name, p in sorted(module.named_parameters()):
             if name.endswith("pos_embedding"):
                 continue
-            noise = torch.randn(p.shape, generator=g, dtype=torch.float32) * 0.02
+            noise = torch.randn(p.shape, generator=g, dtype=torch.float32)
+            if strong:
+                std = (1.0 / (p[0].numel() ** 0.5)) if p.dim() >= 2 else 0.1
+            else:
+                std = 0.02
             is_ln_weight = name.endswith("weight") and p.dim() == 1
-            p.copy_((1.0 + noise) if is_ln_weight else noise)
+            p.copy_((1.0 + noise * std) if is_ln_weight else noise * std)
 
 
-def build_reference(cfg: DiTConfig, seed: int = 0, dtype: str = "fp32"):
+def build_reference(cfg: DiTConfig, seed: int = 0, dtype: str = "fp32", strong: bool = False):
     """Returns (control_model, main_model): reference ControlDiffusionTransformer / DiffusionTransformer."""
     sat_shim.install()
     from landiff.diffusion import dit_video_concat as ref  # the unchanged reference module
 
     ctrl = ref.ControlDiffusionTransformer(**copy.deepcopy(_params(cfg, cfg.control_layers, True)), dtype=dtype)
     main = ref.DiffusionTransformer(**copy.deepcopy(_params(cfg, cfg.main_layers, False)), dtype=dtype)
-    seeded_init_(ctrl, seed)
-    seeded_init_(main, seed + 1)
+    seeded_init_(ctrl, seed, strong)
+    seeded_init_(main, seed + 1, strong)
     ctrl.eval()
     main.eval()
     return ctrl, main

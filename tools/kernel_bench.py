@@ -1,0 +1,128 @@
+"""Per-kernel timing at the full 49-frame 480x720 shape (N=17776 tokens, d=1920, 30 heads), CUDA events on the
+launching stream, L2 flushed between iterations.  Prints achieved TFLOP/s / GB/s against MEASURED_PEAKS.json.
+
+usage: python tools/kernel_bench.py [gemm] [attn] [rows] [--batch 2] [--iters 5]
+"""
+import argparse
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from landiff_b200 import ops  # noqa: E402
+from landiff_b200._C import EPI_BIAS_GELU, EPI_GATED_RESID, EPI_NONE, EPI_QKV  # noqa: E402
+
+dev = "cuda"
+
+
+def peaks():
+    try:
+        p = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        return p["bf16_tflops"], p["hbm_gbs"], "measured"
+    except Exception:
+        return 1590.0, 6650.0, "fallback"
+
+
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    _flush.zero_()
+
+
+WARMUP = [3]
+
+
+def timeit(fn, iters, warmup=None):
+    warmup = WARMUP[0] if warmup is None else min(warmup, WARMUP[0])
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush_l2()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("cases", nargs="*", default=["gemm", "attn", "rows"])
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--ntok", type=int, default=17776)
+    ap.add_argument("--warmup", type=int, default=3)
+    a = ap.parse_args()
+    WARMUP[0] = a.warmup
+    tf_peak, bw_peak, how = peaks()
+    B, N, D, H, TL = a.batch, a.ntok, 1920, 30, 226
+    M = B * N
+    print(f"device {torch.cuda.get_device_name(0)}; peaks {tf_peak} TF/s {bw_peak} GB/s ({how}); B={B} N={N} M={M}", flush=True)
+    torch.manual_seed(0)
+    x = (torch.randn(M, D, device=dev) * 0.5).bfloat16()
+    mod = torch.randn(B, 12, D, device=dev) * 0.1
+    if "gemm" in a.cases:
+        def rnd(n, k):
+            return (torch.randn(n, k, device=dev) * 0.02).bfloat16()
+        w_qkv, w_o, w_1, w_2 = rnd(3 * D, D), rnd(D, D), rnd(4 * D, D), rnd(D, 4 * D)
+        b_qkv, b_o, b_1, b_2 = [(torch.randn(n, device=dev) * 0.02).bfloat16() for n in (3 * D, D, 4 * D, D)]
+        lnp = [torch.ones(64, device=dev).bfloat16(), torch.zeros(64, device=dev).bfloat16()] * 2
+        q = torch.empty(B, H, N, 64, device=dev, dtype=torch.bfloat16)
+        k, v = torch.empty_like(q), torch.empty_like(q)
+        h1 = torch.empty(M, 4 * D, device=dev, dtype=torch.bfloat16)
+        hid = x.clone()
+        cases = [
+            ("qkv   M x5760x1920", 2 * M * 3 * D * D, lambda: ops.gemm(x, w_qkv, epilogue=EPI_QKV, bias=b_qkv, rows_per_batch=N, qkv=(q, k, v), qk_ln=lnp, heads=H)),
+            ("oproj M x1920x1920", 2 * M * D * D, lambda: ops.gemm(x, w_o, epilogue=EPI_GATED_RESID, bias=b_o, rows_per_batch=N, text_len=TL, resid=hid, out=hid, gate_img=mod[:, 2], gate_txt=mod[:, 8], mod_batch_stride=12 * D)),
+            ("fc1   M x7680x1920", 2 * M * 4 * D * D, lambda: ops.gemm(x, w_1, epilogue=EPI_BIAS_GELU, bias=b_1, out=h1)),
+            ("fc2   M x1920x7680", 2 * M * 4 * D * D, lambda: ops.gemm(h1, w_2, epilogue=EPI_GATED_RESID, bias=b_2, rows_per_batch=N, text_len=TL, resid=hid, out=hid, gate_img=mod[:, 5], gate_txt=mod[:, 11], mod_batch_stride=12 * D)),
+            ("zero  M x1920x1920", 2 * M * D * D, lambda: ops.gemm(x, w_o, epilogue=EPI_NONE, out=hid)),
+        ]
+        for name, flops, fn in cases:
+            ms = timeit(fn, a.iters)
+            tf = flops / ms / 1e9
+            print(f"  gemm {name}: {ms:8.3f} ms  {tf:7.1f} TFLOP/s  {tf / tf_peak:.3f} of {how} peak", flush=True)
+        mm = lambda: torch.matmul(x, w_1.T)  # cuBLAS reference point (not the product path)
+        ms = timeit(mm, a.iters)
+        print(f"  [cuBLAS fc1 for scale: {ms:8.3f} ms {2 * M * 4 * D * D / ms / 1e9:7.1f} TFLOP/s]", flush=True)
+    if "attn" in a.cases:
+        q = torch.randn(B, H, N, 64, device=dev).bfloat16()
+        k = torch.randn(B, H, N, 64, device=dev).bfloat16()
+        v = torch.randn(B, H, N, 64, device=dev).bfloat16()
+        out = torch.empty(B, N, H * 64, device=dev, dtype=torch.bfloat16)
+        flops = 4.0 * B * H * N * N * 64
+        for variant in (0, 1):
+            ms = timeit(lambda: ops.attention(q, k, v, out=out, variant=variant), a.iters, warmup=2)
+            tf = flops / ms / 1e9
+            print(f"  attn variant {variant}: {ms:8.3f} ms  {tf:7.1f} TFLOP/s  {tf / tf_peak:.3f} of {how} peak", flush=True)
+        ms = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), a.iters, warmup=2)
+        print(f"  [torch SDPA for scale: {ms:8.3f} ms {flops / ms / 1e9:7.1f} TFLOP/s]", flush=True)
+    if "rows" in a.cases:
+        w = torch.ones(D, device=dev).bfloat16()
+        b = torch.zeros(D, device=dev).bfloat16()
+        out = torch.empty_like(x)
+        ms = timeit(lambda: ops.layernorm_modulate(x, w, b, 1e-5, mod[:, 0], mod[:, 1], mod[:, 6], mod[:, 7], 12 * D, B, N, 0, TL, out=out), a.iters)
+        gb = 2 * M * D * 2 / 1e9
+        print(f"  layernorm_modulate: {ms:8.3f} ms  {gb / ms * 1e3:7.1f} GB/s  {gb / ms * 1e3 / bw_peak:.3f} of {how} peak", flush=True)
+        xl = torch.randn(1, 13, 16, 60, 90, device=dev)
+        nu = torch.randn(1, 13, 16, 60, 90, device=dev).bfloat16()
+        n = xl.numel()
+        ms = timeit(lambda: ops.sampler_update(xl, nu, nu, xl, xl, c_skip=.3, c_out=-.9, cfg=3., m1=1., m2=1., m3=1., m4=1., mn=1., mode=1), a.iters)
+        gb = n * (4 * 3 + 2 * 2 + 4 * 2) / 1e9
+        print(f"  sampler_update: {ms:8.4f} ms  {gb / ms * 1e3:7.1f} GB/s", flush=True)
+
+
+if __name__ == "__main__":
+    main()
