@@ -37,7 +37,22 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <bool P_IN_TMEM>
+// 2^x for x <= ~8 on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial, max rel. error
+// 8.8e-5 — far below the bf16 rounding of P): floor via round-down magic add, fraction in [0,1), exponent
+// re-inserted by an integer add.  Offloads part of the softmax exponentials from the 16-op/clk MUFU unit.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -127.0f);
+  float xr;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(xr) : "f"(x), "f"(12582912.0f));  // 1.5 * 2^23: low mantissa bits = floor(x)
+  const float f = x - (xr - 12582912.0f);
+  float p = fmaf(f, 0.077119089663028717f, 0.227564394474029541f);
+  p = fmaf(p, f, 0.695146143436431885f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
+
+// POLY_EVERY = n > 0: every n-th exponential of a row goes to ex2_poly, the others to MUFU.EX2; 0: all MUFU.
+template <bool P_IN_TMEM, int POLY_EVERY>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
             const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -203,9 +218,15 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         for (int i = 0; i < 128; ++i)
           if (i >= valid) s[i] = 0xff800000u;  // -inf
       }
-      float mx = __uint_as_float(s[0]);
+      float mx4[4] = {__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]), __uint_as_float(s[3])};
 #pragma unroll
-      for (int i = 1; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      for (int i = 4; i < 128; i += 4) {  // four independent chains (the compiler fuses pairs into FMNMX3)
+        mx4[0] = fmaxf(mx4[0], __uint_as_float(s[i]));
+        mx4[1] = fmaxf(mx4[1], __uint_as_float(s[i + 1]));
+        mx4[2] = fmaxf(mx4[2], __uint_as_float(s[i + 2]));
+        mx4[3] = fmaxf(mx4[3], __uint_as_float(s[i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
 
       bool need = (j > 0) && ((mx - m_used) * sl2 > kRescaleThreshold);
       if (j == 0) m_used = mx;
@@ -228,17 +249,29 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         m_used = m_new;
       }
       const float msc = m_used * sl2;
-      float sum0 = 0.f, sum1 = 0.f;
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
       uint32_t pk[64];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const float p0 = ex2(fmaf(__uint_as_float(s[2 * i]), sl2, -msc));
-        const float p1 = ex2(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -msc));
-        sum0 += p0;
-        sum1 += p1;
-        pk[i] = pack_bf16x2(p0, p1);
+      for (int i = 0; i < 32; ++i) {
+        float pv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int idx = 4 * i + e;
+          const float x = fmaf(__uint_as_float(s[idx]), sl2, -msc);
+          if constexpr (POLY_EVERY > 0) {
+            pv[e] = ((idx % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x) : ex2(x);
+          } else {
+            pv[e] = ex2(x);
+          }
+        }
+        sum0 += pv[0];
+        sum1 += pv[1];
+        sum2 += pv[2];
+        sum3 += pv[3];
+        pk[2 * i] = pack_bf16x2(pv[0], pv[1]);
+        pk[2 * i + 1] = pack_bf16x2(pv[2], pv[3]);
       }
-      l += sum0 + sum1;
+      l += (sum0 + sum1) + (sum2 + sum3);
       if constexpr (P_IN_TMEM) {
         LD_TMEM_ST32(ts + 0, (pk + 0));
         LD_TMEM_ST32(ts + 32, (pk + 32));
@@ -331,10 +364,10 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(float* __restrict__ o_a
   if ((gid & 15) == 0) lse_acc[row] = m + log2f(wa + wb);
 }
 
-template <bool P_IN_TMEM>
+template <bool P_IN_TMEM, int POLY_EVERY>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& prm,
                        int grid, cudaStream_t st) {
-  auto kern = attn_kernel<P_IN_TMEM>;
+  auto kern = attn_kernel<P_IN_TMEM, POLY_EVERY>;
   static bool attr_set = false;
   if (!attr_set) {
     LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
@@ -385,10 +418,21 @@ extern "C" int ld_attention_bf16(const void* q, const void* k, const void* v, vo
   prm.nkv = nkv;
   prm.scale_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   const int grid = BH * ((nq + 255) / 256);
-  if (variant == 0) return launch_attn<true>(tq, tk, tv, prm, grid, (cudaStream_t)stream);
-  if (variant == 1) return launch_attn<false>(tq, tk, tv, prm, grid, (cudaStream_t)stream);
-  set_error("ld_attention_bf16: unknown variant %d", variant);
-  return LD_ERR_ARG;
+  // variant: bit 0 = P through shared memory instead of TMEM; bits 1.. = exponential split
+  //   0: default (P in TMEM, every 4th exp on the FMA pipe)   1: P via smem, all MUFU
+  //   2: P in TMEM, all MUFU   4: every 3rd exp polynomial   6: every 2nd   8: every 4th (same as 0)
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (variant) {
+    case 0:
+    case 8: return launch_attn<true, 4>(tq, tk, tv, prm, grid, st);
+    case 1: return launch_attn<false, 0>(tq, tk, tv, prm, grid, st);
+    case 2: return launch_attn<true, 0>(tq, tk, tv, prm, grid, st);
+    case 4: return launch_attn<true, 3>(tq, tk, tv, prm, grid, st);
+    case 6: return launch_attn<true, 2>(tq, tk, tv, prm, grid, st);
+    default:
+      set_error("ld_attention_bf16: unknown variant %d", variant);
+      return LD_ERR_ARG;
+  }
 }
 
 extern "C" int ld_attention_merge(float* o_acc, float* lse_acc, const float* o_new, const float* lse_new, void* out_bf16,

@@ -3,7 +3,8 @@
 //   warp 0      : TMA producer  (A 128x64 and W BNx64 boxes, SWIZZLE_128B, STAGES-deep mbarrier ring)
 //   warp 1      : tcgen05.mma issuer (one elected thread; UMMA 128 x BN x 16, fp32 accumulators in TMEM,
 //                 two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//   warps 2..9  : epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global); two warps per TMEM
+//                 lane quadrant split the tile's columns; global operands are fetched before the TMEM wait
 //
 // Both operands are K-major (activations row-major, nn.Linear weights [out,in]) so no transposes are needed.
 // The fused epilogues implement the reference's per-layer elementwise work (bias, GELU-tanh, adaLN-gated
@@ -29,7 +30,7 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 
 struct RowCtx {
   int row;        // A row
@@ -72,65 +73,121 @@ __device__ __forceinline__ void store8_stream(void* base, bool is_f32, int64_t i
 }
 
 // ---- epilogues on a 32-column chunk held by one thread (one output row) -------------------------------------
+// Operands are fetched from global BEFORE the TMEM load is waited on, so their latency overlaps it.
 template <int EPI>
-__device__ __forceinline__ void epilogue32(const ld_gemm_args& p, const RowCtx& rc, int col, const uint32_t* r) {
-  float acc[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(r[i]);
+struct EpiOperands {
+  uint4 bias[4];    // 32 bf16
+  uint4 resid[8];   // 32 bf16 (first 4) or 32 fp32 (all 8)
+  uint4 add2[4];    // 32 bf16
+  float4 gate[8];   // 32 fp32
+  uint4 pos[4];     // 32 bf16
+};
 
+template <int EPI>
+__device__ __forceinline__ void epi_fetch(const ld_gemm_args& p, const RowCtx& rc, int col, EpiOperands<EPI>& o) {
   if constexpr (EPI != LD_EPI_NONE) {
     if (p.bias != nullptr) {
-      const bf16* bias = reinterpret_cast<const bf16*>(p.bias) + col;
+      const uint4* b = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.bias) + col);
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float bv[8];
-        load8_bf16(bias + g * 8, bv);
+      for (int g = 0; g < 4; ++g) o.bias[g] = b[g];
+    } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[g * 8 + i] += bv[i];
-      }
+      for (int g = 0; g < 4; ++g) o.bias[g] = make_uint4(0, 0, 0, 0);
     }
   }
   if (!rc.valid) return;
+  if constexpr (EPI == LD_EPI_GATED_RESID) {
+    const int64_t eidx = rc.out_row * p.ld_out + col;
+    if (p.resid_f32) {
+      const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.resid) + eidx);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) o.resid[g] = r[g];
+    } else {
+      const uint4* r = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.resid) + eidx);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) o.resid[g] = r[g];
+    }
+    if (p.add2 != nullptr) {
+      const uint4* a2 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.add2) + eidx);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) o.add2[g] = a2[g];
+    }
+    const float4* gt = reinterpret_cast<const float4*>((rc.is_text ? p.gate_txt : p.gate_img) +
+                                                       (int64_t)rc.b * p.mod_batch_stride + col);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) o.gate[g] = gt[g];
+  }
+  if constexpr (EPI == LD_EPI_BIAS_POS) {
+    const uint4* ps = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.pos) +
+                                                     (int64_t)(p.tok_offset + rc.t) * p.N + col);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) o.pos[g] = ps[g];
+  }
+}
+
+__device__ __forceinline__ void unpack8_u4(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue32(const ld_gemm_args& p, const RowCtx& rc, int col, const uint32_t* r,
+                                           const EpiOperands<EPI>& o) {
+  if (!rc.valid) return;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(r[i]);
+  if constexpr (EPI != LD_EPI_NONE) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float bv[8];
+      unpack8_u4(o.bias[g], bv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[g * 8 + i] += bv[i];
+    }
+  }
 
   if constexpr (EPI == LD_EPI_NONE || EPI == LD_EPI_BIAS || EPI == LD_EPI_BIAS_GELU) {
     if constexpr (EPI == LD_EPI_BIAS_GELU) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) acc[i] = gelu_tanh(acc[i]);
     }
-    bf16* o = reinterpret_cast<bf16*>(p.out) + rc.out_row * p.ld_out + col;
+    bf16* op = reinterpret_cast<bf16*>(p.out) + rc.out_row * p.ld_out + col;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) store8_bf16(o + g * 8, acc + g * 8);
+    for (int g = 0; g < 4; ++g) store8_bf16(op + g * 8, acc + g * 8);
   } else if constexpr (EPI == LD_EPI_GATED_RESID) {
-    const float* gate = (rc.is_text ? p.gate_txt : p.gate_img) + (int64_t)rc.b * p.mod_batch_stride + col;
     const int64_t eidx = rc.out_row * p.ld_out + col;
-    const bf16* add2 = p.add2 ? reinterpret_cast<const bf16*>(p.add2) + eidx : nullptr;
     const bool rf32 = p.resid_f32 != 0, of32 = p.out_f32 != 0;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float rv[8];
-      load8_stream(p.resid, rf32, eidx + g * 8, rv);
-      const float4 g0 = *reinterpret_cast<const float4*>(gate + g * 8);
-      const float4 g1 = *reinterpret_cast<const float4*>(gate + g * 8 + 4);
+      if (rf32) {
+        const uint4 a = o.resid[2 * g], b = o.resid[2 * g + 1];
+        rv[0] = __uint_as_float(a.x); rv[1] = __uint_as_float(a.y); rv[2] = __uint_as_float(a.z); rv[3] = __uint_as_float(a.w);
+        rv[4] = __uint_as_float(b.x); rv[5] = __uint_as_float(b.y); rv[6] = __uint_as_float(b.z); rv[7] = __uint_as_float(b.w);
+      } else {
+        unpack8_u4(o.resid[g], rv);
+      }
+      const float4 g0 = o.gate[2 * g], g1 = o.gate[2 * g + 1];
       const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
       float ov[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) ov[i] = fmaf(gv[i], acc[g * 8 + i], rv[i]);
-      if (add2 != nullptr) {
+      if (p.add2 != nullptr) {
         float av[8];
-        load8_bf16(add2 + g * 8, av);
+        unpack8_u4(o.add2[g], av);
 #pragma unroll
         for (int i = 0; i < 8; ++i) ov[i] += av[i];
       }
       store8_stream(p.out, of32, eidx + g * 8, ov);
     }
   } else if constexpr (EPI == LD_EPI_BIAS_POS) {
-    const bf16* pos = reinterpret_cast<const bf16*>(p.pos) + (int64_t)(p.tok_offset + rc.t) * p.N + col;
     const int64_t eidx = rc.out_row * p.ld_out + col;
     const bool of32 = p.out_f32 != 0;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float pv[8];
-      load8_bf16(pos + g * 8, pv);
+      unpack8_u4(o.pos[g], pv);
       float ov[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) ov[i] = acc[g * 8 + i] + pv[i];
@@ -143,13 +200,13 @@ __device__ __forceinline__ void epilogue32(const ld_gemm_args& p, const RowCtx& 
     const int tt = g / hw, rem = g - tt * hw;
     const int h = rem / p.Wp, w = rem - h * p.Wp;
     const int H = 2 * p.Hp, W = 2 * p.Wp;
-    bf16* o = reinterpret_cast<bf16*>(p.out);
+    bf16* op = reinterpret_cast<bf16*>(p.out);
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       const int cc = col + i;
       const int c = cc >> 2, pp = (cc >> 1) & 1;
       const int64_t idx = (((int64_t)(rc.b * p.T + tt) * p.C + c) * H + (2 * h + pp)) * W + 2 * w;
-      *reinterpret_cast<uint32_t*>(o + idx) = pack_bf16x2(acc[i], acc[i + 1]);
+      *reinterpret_cast<uint32_t*>(op + idx) = pack_bf16x2(acc[i], acc[i + 1]);
     }
   }
 }
@@ -241,7 +298,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 8);
     }
     fence_barrier_init();
   }
@@ -301,8 +358,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       }
     }
   } else {
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;        // TMEM lane quadrant this warp may access (warp id % 4)
+    const int half = (warp - 2) >> 2;  // two warps share a quadrant and split the tile's columns
     const int row_in_tile = quad * 32 + lane;
+    // column split: QKV works on whole 64-wide heads, everything else on 32-column chunks
+    constexpr int kSplit = (EPI == LD_EPI_QKV) ? ((BN >= 128) ? (BN / 128) * 64 : 64) : (BN / 64) * 32;
+    const int c_begin = half == 0 ? 0 : kSplit;
+    const int c_end = half == 0 ? kSplit : BN;
     int as = 0;
     uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -322,7 +384,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + as * Cfg::ACC_STRIDE;
       if constexpr (EPI == LD_EPI_QKV) {
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 64) {
+        for (int c = c_begin; c < c_end; c += 64) {
           uint32_t r0[32], r1[32];
           LD_TMEM_LD32(taddr + c, r0);
           LD_TMEM_LD32(taddr + c + 32, r1);
@@ -331,11 +393,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
       } else {
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = c_begin; c < c_end; c += 32) {
+          EpiOperands<EPI> ops;
+          epi_fetch<EPI>(p, rc, n0 + c, ops);
           uint32_t r[32];
           LD_TMEM_LD32(taddr + c, r);
           tmem_ld_wait();
-          epilogue32<EPI>(p, rc, n0 + c, r);
+          epilogue32<EPI>(p, rc, n0 + c, r, ops);
         }
       }
       tc_fence_before();

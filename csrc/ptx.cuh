@@ -199,10 +199,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_tanh(float x) {
-  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))  ==  x * sigmoid(2u)
-  const float u = 0.7978845608028654f * x * (1.0f + 0.044715f * x * x);
-  return x / (1.0f + __expf(-2.0f * u));
+  // 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))   — one MUFU.TANH + 4 FMA-pipe ops
+  const float u = x * fmaf(0.0356774081f, x * x, 0.7978845608f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(u), hx);
 }
 
 }  // namespace ld
