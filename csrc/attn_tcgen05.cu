@@ -9,6 +9,7 @@
 //   warps 8-11    softmax for tile 1   bf16 P -> tcgen05.st over S (or swizzled smem) ; lazy O rescale ; epilogue)
 // The softmax of tile t overlaps the MMAs of tile 1-t.  K/V tail columns are masked to -inf; TMA zero-fills
 // out-of-range rows.  Replaces F.scaled_dot_product_attention as reached from dit_video_concat.py:655-664.
+#include <cstdlib>
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -29,6 +30,9 @@ struct AttnParams {
   float* out_f32;   // [BH, nq, 64] or null
   int heads, nq, nkv;
   float scale_log2;
+  int stagger;       // cycles by which query tile 1 starts its softmax after tile 0 (attn2_kernel)
+  int trace_cta;     // PROF: CTA whose event trace is recorded
+  long long* prof;   // per-(CTA, warp) phase cycle counters (profiling variants only)
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -107,48 +111,65 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
 
   if (warp < 4) {
     reg_dealloc<56>();
-    if (warp == 0 && lane == 0) {
+    // warp-uniform code + elect.sync leader: back-to-back UTMALDG / UTCHMMA (see attn2_kernel)
+    if (warp == 0) {
       // ---------------------------------------------------------------- TMA producer
-      mbar_expect_tx(q_full, 2 * kTileBytes);
-      tma_load_3d(sQ, &tmap_q, q_full, 0, q0, bh);
-      tma_load_3d(sQ + kTileBytes, &tmap_q, q_full, 0, q0 + 128, bh);
+      const bool leader = elect_one();
+      if (leader) {
+        mbar_expect_tx(q_full, 2 * kTileBytes);
+        tma_load_3d(sQ, &tmap_q, q_full, 0, q0, bh);
+        tma_load_3d(sQ + kTileBytes, &tmap_q, q_full, 0, q0 + 128, bh);
+      }
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(&k_empty[s], ph ^ 1);
-        mbar_expect_tx(&k_full[s], kTileBytes);
-        tma_load_3d(sK + s * kTileBytes, &tmap_k, &k_full[s], 0, j * 128, bh);
+        if (leader) {
+          mbar_expect_tx(&k_full[s], kTileBytes);
+          tma_load_3d(sK + s * kTileBytes, &tmap_k, &k_full[s], 0, j * 128, bh);
+        }
         mbar_wait(&v_empty[s], ph ^ 1);
-        mbar_expect_tx(&v_full[s], kTileBytes);
-        tma_load_3d(sV + s * kTileBytes, &tmap_v, &v_full[s], 0, j * 128, bh);
+        if (leader) {
+          mbar_expect_tx(&v_full[s], kTileBytes);
+          tma_load_3d(sV + s * kTileBytes, &tmap_v, &v_full[s], 0, j * 128, bh);
+        }
         if (++s == kKS) { s = 0; ph ^= 1; }
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ---------------------------------------------------------------- MMA issuer
+      const bool leader = elect_one();
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);  // B (=V) is N-major
+      const uint64_t qdesc = make_sdesc_sw128(smem_u32(sQ));
+      const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK));
+      const uint64_t vdesc = make_sdesc_sw128(smem_u32(sV));
+      const uint64_t pdesc = make_sdesc_sw128(smem_u32(sP));
       auto issue_s = [&](int t, int stage) {
-        const uint64_t adesc = make_sdesc_sw128(smem_u32(sQ + t * kTileBytes));
-        const uint64_t bdesc = make_sdesc_sw128(smem_u32(sK + stage * kTileBytes));
+        const uint64_t adesc = qdesc + uint32_t(t * (kTileBytes >> 4));
+        const uint64_t bdesc = kdesc + uint32_t(stage * (kTileBytes >> 4));
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_base + t * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[t]);
+          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + t * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[t]);
+        }
       };
       auto issue_pv = [&](int t, int stage, bool first) {
-        const uint64_t bdesc = make_sdesc_sw128(smem_u32(sV + stage * kTileBytes));
+        const uint64_t bdesc = vdesc + uint32_t(stage * (kTileBytes >> 4));
         const uint32_t d = tmem_base + 256 + t * 64;
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t acc = (first && k == 0) ? 0u : 1u;
-          // 16 keys per step: V rows advance 16*128 B = 2048 B (encoded 128)
-          if constexpr (P_IN_TMEM) {
-            umma_ts(d, tmem_base + t * 128 + k * 8, bdesc + 128 * k, idesc_o, acc);
-          } else {
-            const uint64_t adesc = make_sdesc_sw128(smem_u32(sP + t * kPBytes + (k >> 2) * kTileBytes)) + 2 * (k & 3);
-            umma_ss(d, adesc, bdesc + 128 * k, idesc_o, acc);
+          for (int k = 0; k < 8; ++k) {
+            const uint32_t acc = (first && k == 0) ? 0u : 1u;
+            // 16 keys per step: V rows advance 16*128 B = 2048 B (encoded 128)
+            if constexpr (P_IN_TMEM) {
+              umma_ts(d, tmem_base + t * 128 + k * 8, bdesc + 128 * k, idesc_o, acc);
+            } else {
+              const uint64_t adesc = pdesc + uint32_t(t * (kPBytes >> 4) + (k >> 2) * (kTileBytes >> 4) + 2 * (k & 3));
+              umma_ss(d, adesc, bdesc + 128 * k, idesc_o, acc);
+            }
           }
+          umma_commit(&o_done[t]);
         }
-        umma_commit(&o_done[t]);
       };
 
       mbar_wait(q_full, 0);
@@ -156,7 +177,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
       tc_fence_after();
       issue_s(0, 0);
       issue_s(1, 0);
-      umma_commit(&k_empty[0]);
+      if (leader) umma_commit(&k_empty[0]);
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < n_tiles; ++j) {
@@ -179,10 +200,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
         mbar_wait(&p_full[1], jpar);
         tc_fence_after();
         issue_pv(1, s, j == 0);
-        umma_commit(&v_empty[s]);
+        if (leader) umma_commit(&v_empty[s]);
         if (has_next) {
           issue_s(1, sn);
-          umma_commit(&k_empty[sn]);
+          if (leader) umma_commit(&k_empty[sn]);
         }
         s = sn;
         ph = phn;
@@ -331,6 +352,710 @@ attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ 
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Second-generation kernel: 64-key sub-blocks with the score buffer of every query tile DOUBLE-BUFFERED in TMEM.
+//
+// In attn_kernel the chain  softmax(t,j) -> PV(t,j) -> S(t,j+1) -> softmax(t,j+1)  is serial per query tile (P
+// aliases S, so the next S cannot start before the PV that reads P), and the two tiles' exponential phases
+// collide on the 16-op/clk MUFU unit: ~3300 clk per 128 keys against a 2048-clk MUFU floor.  Here S(t,i+2) is
+// issued right after PV(t,i) into the buffer PV(t,i) just released, so S(t,i+1) is always complete when the
+// softmax of sub-block i finishes; the softmax warps never wait for the tensor pipe and the kernel runs at the
+// MUFU (or, with the polynomial split, the issue-slot) bound.
+//   TMEM columns: S/P(t,b) at (2t+b)*64 [0,256) ; O_t at 256+64t [256,384).
+//   K/V still travel as 128-row TMA boxes (two sub-blocks per box).
+constexpr int kKS2 = 4;
+constexpr int kAttn2Smem = 2 * kTileBytes + 2 * kKS2 * kTileBytes + 1024 + 256;
+
+template <int POLY_EVERY, bool PROF>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+             const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                // 2 tiles
+  uint8_t* sK = sQ + 2 * kTileBytes;                 // kKS2 tiles
+  uint8_t* sV = sK + kKS2 * kTileBytes;              // kKS2 tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKS2 * kTileBytes);
+  uint64_t* q_full = bars;               // 1
+  uint64_t* k_full = bars + 1;           // kKS2
+  uint64_t* k_empty = k_full + kKS2;
+  uint64_t* v_full = k_empty + kKS2;
+  uint64_t* v_empty = v_full + kKS2;
+  uint64_t* s_full = v_empty + kKS2;     // [t][b] = 4
+  uint64_t* p_full = s_full + 4;         // [t][b] = 4
+  uint64_t* o_done = p_full + 4;         // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_blocks = (p.nq + 255) / 256;
+  const int bh = blockIdx.x / q_blocks;
+  const int q0 = (blockIdx.x % q_blocks) * 256;
+  const int n_tiles = (p.nkv + 127) / 128;   // TMA boxes
+  const int n_sub = (p.nkv + 63) / 64;       // 64-key sub-blocks
+  // PROF: event trace of one CTA (first 64 sub-blocks): trace[role][i][event], role 0 = MMA issuer, 1/2 = first
+  // softmax warp of tile 0/1
+  long long* trace = nullptr;
+  if constexpr (PROF) {
+    if (p.prof != nullptr && blockIdx.x == p.trace_cta) trace = p.prof + (int64_t)gridDim.x * 96;
+  }
+#define LD_TRACE(role, i, ev)                                                   \
+  if constexpr (PROF) {                                                         \
+    if (trace != nullptr && (i) < 64) trace[((role) * 64 + (i)) * 8 + (ev)] = clock64(); \
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKS2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
+    mbar_init(&o_done[0], 1);
+    mbar_init(&o_done[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Warps 0 and 1 run warp-uniform code and issue through an elect.sync leader: ptxas then emits back-to-back
+  // UTMALDG / UTCHMMA instead of a per-instruction divergence loop (measured: ~100 clk -> 32 clk per MMA).
+  if (warp < 4) {
+    reg_dealloc<56>();
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      const bool leader = elect_one();
+      if (leader) {
+        mbar_expect_tx(q_full, 2 * kTileBytes);
+        tma_load_3d(sQ, &tmap_q, q_full, 0, q0, bh);
+        tma_load_3d(sQ + kTileBytes, &tmap_q, q_full, 0, q0 + 128, bh);
+      }
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&k_empty[s], ph ^ 1);
+        if (leader) {
+          mbar_expect_tx(&k_full[s], kTileBytes);
+          tma_load_3d(sK + s * kTileBytes, &tmap_k, &k_full[s], 0, j * 128, bh);
+        }
+        mbar_wait(&v_empty[s], ph ^ 1);
+        if (leader) {
+          mbar_expect_tx(&v_full[s], kTileBytes);
+          tma_load_3d(sV + s * kTileBytes, &tmap_v, &v_full[s], 0, j * 128, bh);
+        }
+        if (++s == kKS2) { s = 0; ph ^= 1; }
+      }
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer
+      const bool leader = elect_one();
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);  // B (=V) is N-major
+      const uint64_t qdesc = make_sdesc_sw128(smem_u32(sQ));
+      const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK));
+      const uint64_t vdesc = make_sdesc_sw128(smem_u32(sV));
+      // descriptor address units are 16 B: ring stage = 1024, 64-row half = 512, query tile = 1024
+      // S(t, i) = Q_t K_i^T into buffer i&1; K sub-block i = rows [64*(i&1), +64) of ring stage (i>>1)%kKS2
+      auto issue_s = [&](int t, int i) {
+        const uint64_t adesc = qdesc + uint32_t(t * (kTileBytes >> 4));
+        const uint64_t bdesc = kdesc + uint32_t(((i >> 1) % kKS2) * (kTileBytes >> 4) + (i & 1) * (kTileBytes >> 5));
+        const uint32_t d = tmem_base + (2 * t + (i & 1)) * 64;
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[2 * t + (i & 1)]);
+        }
+      };
+      // O_t += P(t,i) V_i ; P: 128 lanes x 64 keys bf16 = 32 TMEM columns over S(t, i&1)
+      auto issue_pv = [&](int t, int i) {
+        const uint64_t bdesc = vdesc + uint32_t(((i >> 1) % kKS2) * (kTileBytes >> 4) + (i & 1) * (kTileBytes >> 5));
+        const uint32_t d = tmem_base + 256 + t * 64;
+        const uint32_t a = tmem_base + (2 * t + (i & 1)) * 64;
+        if (leader) {
+          // 16 keys per step: 16 rows x 128 B = 2048 B (encoded 128)
+          umma_ts(d, a, bdesc, idesc_o, i != 0);
+#pragma unroll
+          for (int k = 1; k < 4; ++k) umma_ts(d, a + k * 8, bdesc + 128 * k, idesc_o, 1u);
+          umma_commit(&o_done[t]);
+        }
+      };
+      auto k_wait = [&](int tile) { mbar_wait(&k_full[tile % kKS2], (tile / kKS2) & 1); };
+      auto v_wait = [&](int tile) { mbar_wait(&v_full[tile % kKS2], (tile / kKS2) & 1); };
+
+      mbar_wait(q_full, 0);
+      k_wait(0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      if (n_sub > 1) {
+        issue_s(0, 1);
+        issue_s(1, 1);
+      }
+      if (leader) umma_commit(&k_empty[0]);
+      long long w_kv = 0, w_p0 = 0, w_p1 = 0, t_all = 0, w_ipv = 0, w_is = 0;
+      if constexpr (PROF) t_all = clock64();
+      for (int i = 0; i < n_sub; ++i) {
+        const int b = i & 1;
+        const uint32_t par = (i >> 1) & 1;
+        const bool has_next = (i + 2) < n_sub;
+        long long c0 = 0;
+        if constexpr (PROF) c0 = clock64();
+        if (b == 0) v_wait(i >> 1);
+        if (has_next && b == 0) k_wait((i + 2) >> 1);
+        if constexpr (PROF) { const long long c1 = clock64(); w_kv += c1 - c0; c0 = c1; }
+        // tile 0
+        mbar_wait(&p_full[0 + b], par);
+        if constexpr (PROF) { const long long c1 = clock64(); w_p0 += c1 - c0; c0 = c1; }
+        if (leader) { LD_TRACE(0, i, 0); }
+        tc_fence_after();
+        issue_pv(0, i);
+        if constexpr (PROF) { const long long c1 = clock64(); w_ipv += c1 - c0; c0 = c1; }
+        if (has_next) issue_s(0, i + 2);
+        if constexpr (PROF) { const long long c1 = clock64(); w_is += c1 - c0; c0 = c1; }
+        if (leader) { LD_TRACE(0, i, 1); }
+        // tile 1
+        if constexpr (PROF) c0 = clock64();
+        mbar_wait(&p_full[2 + b], par);
+        if constexpr (PROF) w_p1 += clock64() - c0;
+        if (leader) { LD_TRACE(0, i, 2); }
+        tc_fence_after();
+        issue_pv(1, i);
+        if (leader && (b == 1 || i == n_sub - 1)) umma_commit(&v_empty[(i >> 1) % kKS2]);
+        if (has_next) {
+          issue_s(1, i + 2);
+          if (leader && (b == 1 || i + 2 == n_sub - 1)) umma_commit(&k_empty[((i + 2) >> 1) % kKS2]);
+        }
+        if (leader) { LD_TRACE(0, i, 3); }
+      }
+      if constexpr (PROF) {
+        if (leader && p.prof != nullptr) {
+          long long* d = p.prof + ((int64_t)blockIdx.x * 12 + 1) * 8;
+          d[0] = w_kv; d[1] = w_p0; d[2] = w_p1; d[3] = clock64() - t_all; d[4] = w_ipv; d[5] = w_is;
+        }
+      }
+    }
+  } else {
+    reg_alloc<208>();
+    // ------------------------------------------------------------------ softmax / correction / epilogue
+    const int t = (warp - 4) >> 2;        // query tile 0/1
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    const int q_row = q0 + t * 128 + row_in_tile;
+    const uint32_t lane_base = uint32_t(quad * 32) << 16;
+    const uint32_t ts = tmem_base + lane_base + t * 128;       // S(t,0); S(t,1) is 64 columns further
+    const uint32_t to = tmem_base + lane_base + 256 + t * 64;  // O_t
+    const float sl2 = p.scale_log2;
+
+    float m_used = -INFINITY;  // raw-score units
+    float l = 0.f;
+    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+    long long tp = 0;
+#define LD_PROF(slot)                                  \
+  if constexpr (PROF) {                                \
+    const long long now = clock64();                   \
+    prof_acc[slot] += now - tp;                        \
+    tp = now;                                          \
+  }
+    if (t == 1 && p.stagger > 0) {
+      // The two query tiles share each SMSP's MUFU unit.  Their phase offset is preserved by the dynamics (the
+      // tile that enters its exponential phase later is slowed by exactly the overlap), so start tile 1 half a
+      // period late: one tile's exponentials then overlap the other's load / max / store phases for the whole run.
+      mbar_wait(&s_full[2], 0);
+      const long long t_start = clock64();
+      while (clock64() - t_start < p.stagger) {
+      }
+    }
+    if constexpr (PROF) tp = clock64();
+    for (int i = 0; i < n_sub; ++i) {
+      const int b = i & 1;
+      const uint32_t tsb = ts + b * 64;
+      mbar_wait(&s_full[2 * t + b], (i >> 1) & 1);
+      tc_fence_after();
+      LD_PROF(0);
+      if (quad == 0 && lane == 0) { LD_TRACE(1 + t, i, 0); }
+      uint32_t s[64];
+      LD_TMEM_LD32(tsb + 0, (s + 0));
+      LD_TMEM_LD32(tsb + 32, (s + 32));
+      tmem_ld_wait();
+      LD_PROF(1);
+      if (quad == 0 && lane == 0) { LD_TRACE(1 + t, i, 1); }
+      const int valid = p.nkv - i * 64;
+      if (valid < 64) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (c >= valid) s[c] = 0xff800000u;  // -inf
+      }
+      float mx4[4] = {__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]), __uint_as_float(s[3])};
+#pragma unroll
+      for (int c = 4; c < 64; c += 4) {
+        mx4[0] = fmaxf(mx4[0], __uint_as_float(s[c]));
+        mx4[1] = fmaxf(mx4[1], __uint_as_float(s[c + 1]));
+        mx4[2] = fmaxf(mx4[2], __uint_as_float(s[c + 2]));
+        mx4[3] = fmaxf(mx4[3], __uint_as_float(s[c + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+
+      bool need = (i > 0) && ((mx - m_used) * sl2 > kRescaleThreshold);
+      if (i == 0) m_used = mx;
+      if (__any_sync(0xffffffffu, need)) {
+        // lazy correction: bring O_t and l to the new reference maximum (whole warp, tcgen05.ld/st are collective)
+        const float m_new = fmaxf(m_used, mx);
+        const float alpha = ex2((m_used - m_new) * sl2);
+        mbar_wait(&o_done[t], (i - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t o[32];
+          LD_TMEM_LD32(to + c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+          LD_TMEM_ST32(to + c, o);
+        }
+        l *= alpha;
+        m_used = m_new;
+      }
+      const float msc = m_used * sl2;
+      LD_PROF(2);
+      if (quad == 0 && lane == 0) { LD_TRACE(1 + t, i, 2); }
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float pv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int idx = 4 * c + e;
+          const float x = fmaf(__uint_as_float(s[idx]), sl2, -msc);
+          if constexpr (POLY_EVERY > 0) {
+            pv[e] = ((idx % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x) : ex2(x);
+          } else {
+            pv[e] = ex2(x);
+          }
+        }
+        sum0 += pv[0];
+        sum1 += pv[1];
+        sum2 += pv[2];
+        sum3 += pv[3];
+        pk[2 * c] = pack_bf16x2(pv[0], pv[1]);
+        pk[2 * c + 1] = pack_bf16x2(pv[2], pv[3]);
+      }
+      l += (sum0 + sum1) + (sum2 + sum3);
+      LD_PROF(3);
+      if (quad == 0 && lane == 0) { LD_TRACE(1 + t, i, 3); }
+      LD_TMEM_ST32(tsb, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[2 * t + b]);
+      LD_PROF(4);
+      if (quad == 0 && lane == 0) { LD_TRACE(1 + t, i, 4); }
+    }
+
+    // epilogue: O / l
+    // the softmax may run up to two PVs ahead of the tensor pipe: pass the phases in order (parity aliasing)
+    if (n_sub >= 2) mbar_wait(&o_done[t], (n_sub - 2) & 1);
+    mbar_wait(&o_done[t], (n_sub - 1) & 1);
+    tc_fence_after();
+    if constexpr (PROF) {
+      if (lane == 0 && p.prof != nullptr) {
+        long long* d = p.prof + ((int64_t)blockIdx.x * 12 + warp) * 8;
+        for (int e = 0; e < 6; ++e) d[e] = prof_acc[e];
+      }
+    }
+    const float inv_l = 1.0f / l;
+    const bool valid_row = q_row < p.nq;
+    const int bb = bh / p.heads, h = bh - bb * p.heads;
+    bf16* orow = p.out + ((int64_t)bb * p.nq + q_row) * (p.heads * 64) + h * 64;
+#pragma unroll
+    for (int c = 0; c < 64; c += 32) {
+      uint32_t o[32];
+      LD_TMEM_LD32(to + c, o);
+      tmem_ld_wait();
+      if (valid_row) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[g * 8 + e]) * inv_l;
+          uint4 v;
+          v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+          v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(orow + c + g * 8) = v;
+          if (p.out_f32 != nullptr) {
+            float* of = p.out_f32 + ((int64_t)bh * p.nq + q_row) * 64 + c + g * 8;
+            *reinterpret_cast<float4*>(of) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(of + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          }
+        }
+      }
+    }
+    if (valid_row && p.lse != nullptr) p.lse[(int64_t)bh * p.nq + q_row] = m_used * sl2 + log2f(l);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// Third-generation kernel: FOUR independent online-softmax streams per CTA, 16 softmax warps (4 per SMSP).
+//
+// Measured on B200 (tools/softmax_mix_bench.cu): one warp alone runs the exponential mix (FFMA, MUFU.EX2, FADD,
+// F2FP) at ~12 clk/element because its in-order issue cannot overlap MUFU with the dependent ops; two warps per
+// SMSP reach 8.5 and three or more 8.2 — the MUFU limit (8).  So the kernel needs >= 3 warps per SMSP that have
+// exponentials to do at any time.  TMEM (512 columns) cannot hold more than two 128-row query tiles with their
+// accumulators, so each query tile is served by TWO streams that split the keys by 64-key sub-block parity:
+// stream (t, b) owns sub-blocks i = b, b+2, ... of query tile t with its own score buffer S, its own output
+// accumulator O and its own running (max, sum); the two streams of a tile are merged by log-sum-exp in the
+// epilogue.  While one stream waits for the tensor pipe (PV then the next S) the other three keep MUFU busy.
+//   warp 0: TMA producer   warp 1: MMA issuer   (2, 3 idle)   warps 4-19: softmax, stream = (warp-4)/4, TMEM
+//   quadrant = warp%4.  640 threads start at 96 registers; the control warpgroup drops to 48 and the softmax
+//   warpgroups rise to 104 (setmaxnreg.inc only draws on registers released inside the CTA: 6144 >= 4096).
+//   TMEM columns: S/P(stream) at 64*stream [0,256) ; O(stream) at 256 + 64*stream [256,512)
+constexpr int kAttn3Threads = 640;
+constexpr int kKS3 = 4;
+constexpr int kAttn3Smem = 2 * kTileBytes + 2 * kKS3 * kTileBytes + 2 * 128 * 2 * 8 /*(m,l) exchange*/ + 1024 + 256;
+
+template <int POLY_EVERY, bool PROF>
+__global__ void __launch_bounds__(kAttn3Threads, 1)
+attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+             const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                // 2 tiles
+  uint8_t* sK = sQ + 2 * kTileBytes;                 // kKS3 tiles
+  uint8_t* sV = sK + kKS3 * kTileBytes;              // kKS3 tiles
+  float2* sML = reinterpret_cast<float2*>(sV + kKS3 * kTileBytes);   // [stream][128] (m * scale_log2, l)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sML + 4 * 128);
+  uint64_t* q_full = bars;               // 1
+  uint64_t* k_full = bars + 1;           // kKS3
+  uint64_t* k_empty = k_full + kKS3;
+  uint64_t* v_full = k_empty + kKS3;
+  uint64_t* v_empty = v_full + kKS3;
+  uint64_t* s_full = v_empty + kKS3;     // [stream] = 4
+  uint64_t* p_full = s_full + 4;         // [stream] = 4
+  uint64_t* o_done = p_full + 4;         // [stream] = 4
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_blocks = (p.nq + 255) / 256;
+  const int bh = blockIdx.x / q_blocks;
+  const int q0 = (blockIdx.x % q_blocks) * 256;
+  const int n_tiles = (p.nkv + 127) / 128;   // TMA boxes
+  const int n_sub = (p.nkv + 63) / 64;       // 64-key sub-blocks
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKS3; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Warps 0 and 1 run warp-uniform code and issue through an elect.sync leader: ptxas then emits back-to-back
+  // UTMALDG / UTCHMMA instead of a per-instruction divergence loop (measured: ~100 clk -> 32 clk per MMA).
+  if (warp < 4) reg_dealloc<48>();
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(q_full, 2 * kTileBytes);
+      tma_load_3d(sQ, &tmap_q, q_full, 0, q0, bh);
+      tma_load_3d(sQ + kTileBytes, &tmap_q, q_full, 0, q0 + 128, bh);
+    }
+    int s = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&k_empty[s], ph ^ 1);
+      if (leader) {
+        mbar_expect_tx(&k_full[s], kTileBytes);
+        tma_load_3d(sK + s * kTileBytes, &tmap_k, &k_full[s], 0, j * 128, bh);
+      }
+      mbar_wait(&v_empty[s], ph ^ 1);
+      if (leader) {
+        mbar_expect_tx(&v_full[s], kTileBytes);
+        tma_load_3d(sV + s * kTileBytes, &tmap_v, &v_full[s], 0, j * 128, bh);
+      }
+      if (++s == kKS3) { s = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);  // B (=V) is N-major
+    const uint64_t qdesc = make_sdesc_sw128(smem_u32(sQ));
+    const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK));
+    const uint64_t vdesc = make_sdesc_sw128(smem_u32(sV));
+    // descriptor address units are 16 B: ring stage = 1024, 64-row half = 512, query tile = 1024
+    // S(t, i) = Q_t K_i^T into the score buffer of stream 2t + (i&1); K sub-block i = rows [64*(i&1), +64) of ring
+    // stage (i>>1) % kKS3
+    auto issue_s = [&](int t, int i) {
+      const uint64_t adesc = qdesc + uint32_t(t * (kTileBytes >> 4));
+      const uint64_t bdesc = kdesc + uint32_t(((i >> 1) % kKS3) * (kTileBytes >> 4) + (i & 1) * (kTileBytes >> 5));
+      const int st = 2 * t + (i & 1);
+      const uint32_t d = tmem_base + st * 64;
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[st]);
+      }
+    };
+    // O(stream) += P(t,i) V_i ; P: 128 lanes x 64 keys bf16 = 32 TMEM columns over S(stream)
+    auto issue_pv = [&](int t, int i) {
+      const uint64_t bdesc = vdesc + uint32_t(((i >> 1) % kKS3) * (kTileBytes >> 4) + (i & 1) * (kTileBytes >> 5));
+      const int st = 2 * t + (i & 1);
+      const uint32_t d = tmem_base + 256 + st * 64;
+      const uint32_t a = tmem_base + st * 64;
+      if (leader) {
+        // 16 keys per step: 16 rows x 128 B = 2048 B (encoded 128)
+        umma_ts(d, a, bdesc, idesc_o, i >= 2);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) umma_ts(d, a + k * 8, bdesc + 128 * k, idesc_o, 1u);
+        umma_commit(&o_done[st]);
+      }
+    };
+    auto k_wait = [&](int tile) { mbar_wait(&k_full[tile % kKS3], (tile / kKS3) & 1); };
+    auto v_wait = [&](int tile) { mbar_wait(&v_full[tile % kKS3], (tile / kKS3) & 1); };
+
+    mbar_wait(q_full, 0);
+    k_wait(0);
+    tc_fence_after();
+    issue_s(0, 0);
+    issue_s(1, 0);
+    if (n_sub > 1) {
+      issue_s(0, 1);
+      issue_s(1, 1);
+    }
+    if (leader) umma_commit(&k_empty[0]);
+    long long w_kv = 0, w_p0 = 0, w_p1 = 0, t_all = 0;
+    if constexpr (PROF) t_all = clock64();
+    for (int i = 0; i < n_sub; ++i) {
+      const int b = i & 1;
+      const uint32_t par = (i >> 1) & 1;
+      const bool has_next = (i + 2) < n_sub;
+      long long c0 = 0;
+      if constexpr (PROF) c0 = clock64();
+      if (b == 0) v_wait(i >> 1);
+      if (has_next && b == 0) k_wait((i + 2) >> 1);
+      if constexpr (PROF) { const long long c1 = clock64(); w_kv += c1 - c0; c0 = c1; }
+      // tile 0
+      mbar_wait(&p_full[0 + b], par);
+      if constexpr (PROF) { const long long c1 = clock64(); w_p0 += c1 - c0; c0 = c1; }
+      tc_fence_after();
+      issue_pv(0, i);
+      if (has_next) issue_s(0, i + 2);
+      // tile 1
+      if constexpr (PROF) c0 = clock64();
+      mbar_wait(&p_full[2 + b], par);
+      if constexpr (PROF) w_p1 += clock64() - c0;
+      tc_fence_after();
+      issue_pv(1, i);
+      if (leader && (b == 1 || i == n_sub - 1)) umma_commit(&v_empty[(i >> 1) % kKS3]);
+      if (has_next) {
+        issue_s(1, i + 2);
+        if (leader && (b == 1 || i + 2 == n_sub - 1)) umma_commit(&k_empty[((i + 2) >> 1) % kKS3]);
+      }
+    }
+    if constexpr (PROF) {
+      if (leader && p.prof != nullptr) {
+        long long* d = p.prof + ((int64_t)blockIdx.x * 20 + 1) * 8;
+        d[0] = w_kv; d[1] = w_p0; d[2] = w_p1; d[3] = clock64() - t_all;
+      }
+    }
+  } else if (warp >= 4) {
+    reg_alloc<104>();   // 16 warps x 32 x 8 = 4096 <= the 6144 registers released by the control warpgroup
+    // -------------------------------------------------------------------- softmax / correction / epilogue
+    const int st = (warp - 4) >> 2;       // stream
+    const int t = st >> 1;                // query tile
+    const int b = st & 1;                 // sub-block parity served by this stream
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    const int q_row = q0 + t * 128 + row_in_tile;
+    const uint32_t lane_base = uint32_t(quad * 32) << 16;
+    const uint32_t ts = tmem_base + lane_base + st * 64;         // S / P of this stream
+    const uint32_t to = tmem_base + lane_base + 256 + st * 64;   // O of this stream
+    const float sl2 = p.scale_log2;
+
+    float m_used = -INFINITY;  // raw-score units
+    float l = 0.f;
+    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+    long long tp = 0;
+    if constexpr (PROF) tp = clock64();
+    int kk = 0;   // blocks done by this stream
+    for (int i = b; i < n_sub; i += 2, ++kk) {
+      mbar_wait(&s_full[st], kk & 1);
+      tc_fence_after();
+      LD_PROF(0);
+      uint32_t s[64];
+      LD_TMEM_LD32(ts + 0, (s + 0));
+      LD_TMEM_LD32(ts + 32, (s + 32));
+      tmem_ld_wait();
+      LD_PROF(1);
+      const int valid = p.nkv - i * 64;
+      if (valid < 64) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (c >= valid) s[c] = 0xff800000u;  // -inf
+      }
+      float mx4[4] = {__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]), __uint_as_float(s[3])};
+#pragma unroll
+      for (int c = 4; c < 64; c += 4) {
+        mx4[0] = fmaxf(mx4[0], __uint_as_float(s[c]));
+        mx4[1] = fmaxf(mx4[1], __uint_as_float(s[c + 1]));
+        mx4[2] = fmaxf(mx4[2], __uint_as_float(s[c + 2]));
+        mx4[3] = fmaxf(mx4[3], __uint_as_float(s[c + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+
+      bool need = (kk > 0) && ((mx - m_used) * sl2 > kRescaleThreshold);
+      if (kk == 0) m_used = mx;
+      if (__any_sync(0xffffffffu, need)) {
+        // lazy correction: bring O and l of this stream to the new reference maximum (whole warp: tcgen05.ld/st are
+        // collective).  s_full(kk) completing implies PV(kk-1) completed (commit order), so O is quiescent.
+        const float m_new = fmaxf(m_used, mx);
+        const float alpha = ex2((m_used - m_new) * sl2);
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 8) {   // rare path: 8 columns at a time keeps it out of the main loop's registers
+          uint32_t o[8];
+          LD_TMEM_LD8(to + c, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+          LD_TMEM_ST8(to + c, o);
+        }
+        l *= alpha;
+        m_used = m_new;
+      }
+      const float msc = m_used * sl2;
+      LD_PROF(2);
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float pv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int idx = 4 * c + e;
+          const float x = fmaf(__uint_as_float(s[idx]), sl2, -msc);
+          if constexpr (POLY_EVERY > 0) {
+            pv[e] = ((idx % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x) : ex2(x);
+          } else {
+            pv[e] = ex2(x);
+          }
+        }
+        sum0 += pv[0];
+        sum1 += pv[1];
+        sum2 += pv[2];
+        sum3 += pv[3];
+        pk[2 * c] = pack_bf16x2(pv[0], pv[1]);
+        pk[2 * c + 1] = pack_bf16x2(pv[2], pv[3]);
+      }
+      l += (sum0 + sum1) + (sum2 + sum3);
+      LD_PROF(3);
+      LD_TMEM_ST32(ts, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[st]);
+      LD_PROF(4);
+    }
+
+    // ---- epilogue: merge the two streams of this query tile by log-sum-exp; stream b writes output columns
+    //      [32b, 32b+32) of the head
+    if (kk > 0) {
+      mbar_wait(&o_done[st], (kk - 1) & 1);
+      tc_fence_after();
+    }
+    if constexpr (PROF) {
+      if (lane == 0 && p.prof != nullptr) {
+        long long* d = p.prof + ((int64_t)blockIdx.x * 20 + warp) * 8;
+        for (int e = 0; e < 6; ++e) d[e] = prof_acc[e];
+      }
+    }
+    sML[st * 128 + row_in_tile] = make_float2(m_used * sl2, l);
+    tc_fence_before();
+    named_bar_sync(1 + t, 256);     // the 8 warps of query tile t
+    tc_fence_after();
+    const float2 other = sML[(st ^ 1) * 128 + row_in_tile];
+    const bool other_has = n_sub > (b ^ 1);   // the sibling stream processed at least one sub-block (uniform)
+    const float m_mine = m_used * sl2, m_oth = other_has ? other.x : -INFINITY;
+    const float m_all = fmaxf(m_mine, m_oth);
+    const float w_mine = (kk > 0) ? ex2(m_mine - m_all) : 0.f;
+    const float w_oth = other_has ? ex2(m_oth - m_all) : 0.f;
+    const float l_all = w_mine * l + w_oth * (other_has ? other.y : 0.f);
+    const float inv_l = 1.0f / l_all;
+    const float f_mine = w_mine * inv_l, f_oth = w_oth * inv_l;
+    const bool valid_row = q_row < p.nq;
+    const int bb = bh / p.heads, h = bh - bb * p.heads;
+    const int c0 = 32 * b;
+    uint32_t oa[32], ob[32];
+    const uint32_t to_oth = tmem_base + lane_base + 256 + (st ^ 1) * 64;
+    if (kk > 0) {
+      LD_TMEM_LD32(to + c0, oa);
+    }
+    if (other_has) {
+      LD_TMEM_LD32(to_oth + c0, ob);
+    }
+    tmem_ld_wait();
+    if (valid_row) {
+      bf16* orow = p.out + ((int64_t)bb * p.nq + q_row) * (p.heads * 64) + h * 64 + c0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float v = 0.f;
+          if (kk > 0) v = __uint_as_float(oa[g * 8 + e]) * f_mine;
+          if (other_has) v = fmaf(__uint_as_float(ob[g * 8 + e]), f_oth, v);
+          f[e] = v;
+        }
+        uint4 v;
+        v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+        v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(orow + g * 8) = v;
+        if (p.out_f32 != nullptr) {
+          float* of = p.out_f32 + ((int64_t)bh * p.nq + q_row) * 64 + c0 + g * 8;
+          *reinterpret_cast<float4*>(of) = make_float4(f[0], f[1], f[2], f[3]);
+          *reinterpret_cast<float4*>(of + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        }
+      }
+      if (b == 0 && p.lse != nullptr) p.lse[(int64_t)bh * p.nq + q_row] = m_all + log2f(l_all);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // (o_acc, lse_acc) <- merge with (o_new, lse_new); log2-domain LSE
 __global__ void __launch_bounds__(256) attn_merge_kernel(float* __restrict__ o_acc, float* __restrict__ lse_acc,
                                                          const float* __restrict__ o_new,
@@ -378,9 +1103,41 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   return LD_OK;
 }
 
+template <int POLY_EVERY, bool PROF = false>
+static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& prm,
+                        int grid, cudaStream_t st) {
+  auto kern = attn2_kernel<POLY_EVERY, PROF>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2Smem));
+    attr_set = true;
+  }
+  kern<<<grid, kAttnThreads, kAttn2Smem, st>>>(tq, tk, tv, prm);
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}
+
+template <int POLY_EVERY, bool PROF = false>
+static int launch_attn3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& prm,
+                        int grid, cudaStream_t st) {
+  auto kern = attn3_kernel<POLY_EVERY, PROF>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3Smem));
+    attr_set = true;
+  }
+  kern<<<grid, kAttn3Threads, kAttn3Smem, st>>>(tq, tk, tv, prm);
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}
+
 }  // namespace ld
 
 using namespace ld;
+
+static long long* g_attn_prof = nullptr;
+// Debug hook (tools/attn_phase_prof.py): per-(CTA, warp) phase cycle counters for the next ld_attention_bf16 calls.
+extern "C" void ld_debug_attn_prof(long long* buf) { g_attn_prof = buf; }
 
 extern "C" int ld_attention_bf16(const void* q, const void* k, const void* v, void* out, float* lse, float* out_f32,
                                  int batch, int heads, int nq, int q_rows, int nkv, int kv_rows, int variant,
@@ -416,6 +1173,16 @@ extern "C" int ld_attention_bf16(const void* q, const void* k, const void* v, vo
   prm.heads = heads;
   prm.nq = nq;
   prm.nkv = nkv;
+  prm.prof = nullptr;
+  prm.trace_cta = 0;
+  {
+    static int stagger = -1;
+    if (stagger < 0) {
+      const char* e = getenv("LD_ATTN_STAGGER");
+      stagger = e ? atoi(e) : 540;
+    }
+    prm.stagger = stagger;
+  }
   prm.scale_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   const int grid = BH * ((nq + 255) / 256);
   // variant: bit 0 = P through shared memory instead of TMEM; bits 1.. = exponential split
@@ -429,6 +1196,27 @@ extern "C" int ld_attention_bf16(const void* q, const void* k, const void* v, vo
     case 2: return launch_attn<true, 0>(tq, tk, tv, prm, grid, st);
     case 4: return launch_attn<true, 3>(tq, tk, tv, prm, grid, st);
     case 6: return launch_attn<true, 2>(tq, tk, tv, prm, grid, st);
+    // second-generation kernel (double-buffered 64-key score blocks): 16 all MUFU, 17/18/19 every 4th/3rd/2nd polynomial
+    case 16:
+      if (g_attn_prof != nullptr) {
+        prm.prof = g_attn_prof;
+        { const char* e = getenv("LD_ATTN_TRACE_CTA"); prm.trace_cta = e ? atoi(e) : 0; }
+        return launch_attn2<0, true>(tq, tk, tv, prm, grid, st);
+      }
+      return launch_attn2<0>(tq, tk, tv, prm, grid, st);
+    case 17: return launch_attn2<4>(tq, tk, tv, prm, grid, st);
+    case 18: return launch_attn2<3>(tq, tk, tv, prm, grid, st);
+    case 19: return launch_attn2<2>(tq, tk, tv, prm, grid, st);
+    // third-generation kernel (four softmax streams): 32 all MUFU, 33/34/35 every 4th/3rd/2nd polynomial
+    case 32:
+      if (g_attn_prof != nullptr) {
+        prm.prof = g_attn_prof;
+        return launch_attn3<0, true>(tq, tk, tv, prm, grid, st);
+      }
+      return launch_attn3<0>(tq, tk, tv, prm, grid, st);
+    case 33: return launch_attn3<4>(tq, tk, tv, prm, grid, st);
+    case 34: return launch_attn3<3>(tq, tk, tv, prm, grid, st);
+    case 35: return launch_attn3<2>(tq, tk, tv, prm, grid, st);
     default:
       set_error("ld_attention_bf16: unknown variant %d", variant);
       return LD_ERR_ARG;

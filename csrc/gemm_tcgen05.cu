@@ -313,49 +313,55 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int num_tiles = num_m * num_n;
   const int num_kb = p.K / Cfg::BK;
 
+  // Producer and MMA warps run warp-uniform code and issue through an elect.sync leader, which ptxas compiles to
+  // back-to-back UTMALDG / UTCHMMA (a `lane == 0` branch costs a divergence loop of ~12 instructions per MMA).
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * Cfg::BM;
-        const int n0 = (tile % num_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
+    const bool leader = elect_one();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * Cfg::BM;
+      const int n0 = (tile % num_n) * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (leader) {
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
           tma_load_2d(sA + s * Cfg::A_BYTES, &tmap_a, &full_bar[s], kb * Cfg::BK, m0);
           tma_load_2d(sB + s * Cfg::B_BYTES, &tmap_b, &full_bar[s], kb * Cfg::BK, n0);
-          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(Cfg::BM, BN);
-      int s = 0;
-      uint32_t ph = 0;
-      int as = 0;
-      uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[as], aph ^ 1);
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_bf16(Cfg::BM, BN);
+    const uint64_t adesc0 = make_sdesc_sw128(smem_u32(sA));
+    const uint64_t bdesc0 = make_sdesc_sw128(smem_u32(sB));
+    int s = 0;
+    uint32_t ph = 0;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint64_t adesc = make_sdesc_sw128(smem_u32(sA + s * Cfg::A_BYTES));
-          const uint64_t bdesc = make_sdesc_sw128(smem_u32(sB + s * Cfg::B_BYTES));
+        const uint64_t adesc = adesc0 + uint32_t(s * (Cfg::A_BYTES >> 4));
+        const uint64_t bdesc = bdesc0 + uint32_t(s * (Cfg::B_BYTES >> 4));
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < Cfg::BK / 16; ++k) {
             // +32 bytes (encoded >>4 = 2) per 16-element K step inside the 128-byte swizzle span
             umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
-          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);
-        if (++as == 2) { as = 0; aph ^= 1; }
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
       }
+      if (leader) umma_commit(&tfull_bar[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
     }
   } else {
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access (warp id % 4)

@@ -96,11 +96,11 @@ def test_gemm_all_epilogues():
     report("gemm UNPATCHIFY", out, y.permute(0, 1, 4, 2, 5, 3, 6).reshape(B, T, Cc, 2 * Hp, 2 * Wp))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 4, 6])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 6, 16, 17, 18, 19, 32, 33, 34, 35])
 def test_attention(variant):
     torch.manual_seed(1)
     for (B, H, nq, nkv) in [(1, 1, 128, 128), (1, 1, 256, 128), (1, 2, 300, 300), (2, 3, 886, 886), (1, 2, 500, 1000),
-                            (1, 4, 4444, 17776)]:
+                            (1, 4, 4444, 17776), (1, 1, 200, 50), (1, 2, 256, 192), (1, 1, 130, 8888)]:
         q = torch.randn(B, H, nq, 64, device=dev).bfloat16()
         k = torch.randn(B, H, nkv, 64, device=dev).bfloat16()
         v = torch.randn(B, H, nkv, 64, device=dev).bfloat16()

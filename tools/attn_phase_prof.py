@@ -1,0 +1,40 @@
+"""Per-phase cycle breakdown of the attention kernel's softmax warps and MMA issuer (debug variant of attn2_kernel).
+usage: python tools/attn_phase_prof.py [N]"""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from landiff_b200 import _C, ops
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 17776
+B, H = 1, 30
+dev = "cuda"
+q = torch.randn(B, H, N, 64, device=dev).bfloat16()
+k = torch.randn(B, H, N, 64, device=dev).bfloat16()
+v = torch.randn(B, H, N, 64, device=dev).bfloat16()
+out = torch.empty(B, N, H * 64, device=dev, dtype=torch.bfloat16)
+grid = B * H * ((N + 255) // 256)
+VAR = int(os.environ.get("LD_ATTN_VARIANT", "32"))
+NW = 20 if VAR >= 32 else 12
+FIRST = 4
+prof_all = torch.zeros(grid * NW * 8 + 3 * 64 * 8, device=dev, dtype=torch.int64)
+prof = prof_all[:grid * NW * 8].view(grid, NW, 8)
+lib = _C.load()
+lib.ld_debug_attn_prof.argtypes = [ctypes.c_void_p]
+lib.ld_debug_attn_prof.restype = None
+ops.attention(q, k, v, out=out, variant=VAR)
+torch.cuda.synchronize()
+lib.ld_debug_attn_prof(prof.data_ptr())
+ops.attention(q, k, v, out=out, variant=VAR)
+torch.cuda.synchronize()
+lib.ld_debug_attn_prof(None)
+n_sub = (N + 63) // 64
+per_warp = n_sub if VAR < 32 else n_sub / 2
+p = prof.double().cpu()
+sm = p[:, FIRST:NW, :5].mean(dim=(0, 1)) / per_warp
+names = ["wait s_full", "tcgen05.ld", "mask+max+rescale", "exp+sum+pack", "st+fence+arrive"]
+print(f"variant {VAR} N={N} n_sub={n_sub}: softmax warp cycles per 64-key sub-block it processes (mean over CTAs and warps)")
+for n, c in zip(names, sm.tolist()):
+    print(f"  {n:20s} {c:8.1f}")
+print(f"  {'total':20s} {sm.sum().item():8.1f}")
+mm = p[:, 1, :4].mean(dim=0) / n_sub
+print("MMA issuer per sub-block (both tiles): wait k/v %.1f  wait p_full[tile 0] %.1f  wait p_full[tile 1] %.1f  loop total %.1f" % tuple(mm.tolist()))

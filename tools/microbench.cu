@@ -32,8 +32,20 @@ __global__ void k(float* out, unsigned long long* cyc, float seed) {
       if (OP == 3) asm volatile("fma.rn.f32x2 %0, %0, %1, %1;" : "+l"(d[i]) : "l"(cc));
       if (OP == 4) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(d[i]) : "l"(cc));
       if (OP == 5) asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(c1), "f"(c2));
-      if (OP == 6) asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(a[i]), "f"(c1));
-      if (OP == 7) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(a[i]), "f"(c1));
+      if (OP == 6) asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(__uint_as_float(u[i])), "f"(c1));
+      if (OP == 7) asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(__uint_as_float(u[i])), "f"(c1));
+      if (OP == 16) asm volatile("prmt.b32 %0, %0, %1, 0x7632;" : "+r"(u[i]) : "r"(__float_as_uint(c1)));
+      if (OP == 17) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(u[i]) : "r"(__float_as_uint(c1)), "r"(__float_as_uint(c2)));
+      if (OP == 18) {  // ex2 + cvt pack interleaved: do they share a pipe?
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+        asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(__uint_as_float(u[i])), "f"(c1));
+      }
+      if (OP == 19) {  // ex2 + (iadd, prmt) interleaved
+        asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+        asm volatile("add.s32 %0, %0, 0x8000;" : "+r"(u[i]));
+        asm volatile("prmt.b32 %0, %0, %1, 0x7632;" : "+r"(u[i]) : "r"(__float_as_uint(c1)));
+      }
+      if (OP == 20) asm volatile("cvt.rn.bf16.f32 %0, %1;" : "=h"(*(unsigned short*)&u[i]) : "f"(__uint_as_float(u[i])));
       if (OP == 8) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(a[i]));
       if (OP == 9) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(c1), "f"(c2));
       if (OP == 10) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(c1));
@@ -72,7 +84,7 @@ void run(const char* name) {
     for (int i = 0; i < 148; ++i) avg += h[i];
     avg /= 148;
     int warps_per_smsp = threads / 128;
-    double instr_per_smsp = (double)ITERS * CHAINS * warps_per_smsp * (OP == 12 ? 2 : 1);
+    double instr_per_smsp = (double)ITERS * CHAINS * warps_per_smsp * (OP == 12 || OP == 18 ? 2 : (OP == 19 ? 3 : 1));
     printf("  %dw/smsp: %6.2f cyc/winstr", warps_per_smsp, avg / instr_per_smsp);
   }
   printf("\n");
@@ -97,5 +109,9 @@ int main() {
   run<14>("shl.b32");
   run<15>("add.s32");
   run<12>("ex2.f32 + fma.f32 interleaved");
+  run<16>("prmt.b32");
+  run<17>("lop3.b32");
+  run<18>("ex2.f32 + cvt.bf16x2 interleaved");
+  run<19>("ex2.f32 + add.s32 + prmt");
   return 0;
 }

@@ -1,0 +1,174 @@
+// Throughput of the softmax exponential phase instruction mix on sm_100a, 1 or 2 warps per SMSP:
+//   per element: FFMA (scale - max), MUFU.EX2, FADD (row sum); per pair: F2FP bf16x2 pack.
+// MODE 0: plain mix   1: packed f32x2 FFMA/FADD   2: no pack   3: no FADD   4: MUFU only   5: every 4th exp polynomial
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+__device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -127.0f);
+  float xr;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(xr) : "f"(x), "f"(12582912.0f));
+  const float f = x - (xr - 12582912.0f);
+  float p = fmaf(f, 0.077119089663028717f, 0.227564394474029541f);
+  p = fmaf(p, f, 0.695146143436431885f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
+
+template <int MODE>
+__global__ void k(const float* in, uint32_t* out, unsigned long long* cyc, float sl2, float msc, int iters) {
+  float s[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) s[i] = in[threadIdx.x * 64 + i];
+  uint32_t acc = 0;
+  float sum0 = 0, sum1 = 0, sum2 = 0, sum3 = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t pk[32];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float pv[4];
+      if (MODE == 1) {
+        unsigned long long a01, a23, sc, ms;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(a01) : "f"(s[4 * c]), "f"(s[4 * c + 1]));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(a23) : "f"(s[4 * c + 2]), "f"(s[4 * c + 3]));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(sc) : "f"(sl2));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(ms) : "f"(-msc));
+        asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a01) : "l"(sc), "l"(ms));
+        asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a23) : "l"(sc), "l"(ms));
+        float x0, x1, x2, x3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(a01));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(x2), "=f"(x3) : "l"(a23));
+        pv[0] = ex2(x0); pv[1] = ex2(x1); pv[2] = ex2(x2); pv[3] = ex2(x3);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x = fmaf(s[4 * c + e], sl2, -msc);
+          if (MODE == 5 && e == 3) pv[e] = ex2_poly(x); else pv[e] = ex2(x);
+        }
+      }
+      if (MODE != 3 && MODE != 4) { sum0 += pv[0]; sum1 += pv[1]; sum2 += pv[2]; sum3 += pv[3]; }
+      if (MODE != 2 && MODE != 4) {
+        __nv_bfloat162 v0 = __floats2bfloat162_rn(pv[0], pv[1]);
+        __nv_bfloat162 v1 = __floats2bfloat162_rn(pv[2], pv[3]);
+        pk[2 * c] = *reinterpret_cast<uint32_t*>(&v0);
+        pk[2 * c + 1] = *reinterpret_cast<uint32_t*>(&v1);
+      } else {
+        pk[2 * c] = __float_as_uint(pv[0]) ^ __float_as_uint(pv[1]);
+        pk[2 * c + 1] = __float_as_uint(pv[2]) ^ __float_as_uint(pv[3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc ^= pk[i];   // 32 LOP3-ish ops of overhead per 64 elements (reported separately)
+    msc += 1e-3f;
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc + __float_as_uint(sum0 + sum1 + sum2 + sum3);
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+// Software-pipelined variant: the FADD / F2FP consumers of chunk c are issued after the FFMA + MUFU of chunk c+1
+// (CH elements per chunk), so a single in-order warp never waits on MUFU result latency.
+// POLY: every POLY-th element uses the FMA-pipe polynomial (0 = none)
+template <int CH, int POLY>
+__global__ void kp(const float* in, uint32_t* out, unsigned long long* cyc, float sl2, float msc, int iters) {
+  float s[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) s[i] = in[threadIdx.x * 64 + i];
+  uint32_t acc = 0;
+  float sum0 = 0, sum1 = 0, sum2 = 0, sum3 = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t pk[32];
+    float pv[2][CH];
+#pragma unroll
+    for (int c = 0; c <= 64 / CH; ++c) {
+      if (c < 64 / CH) {
+#pragma unroll
+        for (int e = 0; e < CH; ++e) {
+          const float x = fmaf(s[c * CH + e], sl2, -msc);
+          if (POLY > 0 && (e % POLY) == POLY - 1) pv[c & 1][e] = ex2_poly(x); else pv[c & 1][e] = ex2(x);
+        }
+      }
+      if (c > 0) {
+        const int cc = c - 1;
+#pragma unroll
+        for (int e = 0; e < CH; e += 4) {
+          float* q = &pv[cc & 1][e];
+          sum0 += q[0]; sum1 += q[1]; sum2 += q[2]; sum3 += q[3];
+          __nv_bfloat162 v0 = __floats2bfloat162_rn(q[0], q[1]);
+          __nv_bfloat162 v1 = __floats2bfloat162_rn(q[2], q[3]);
+          pk[(cc * CH + e) / 2] = *reinterpret_cast<uint32_t*>(&v0);
+          pk[(cc * CH + e) / 2 + 1] = *reinterpret_cast<uint32_t*>(&v1);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc ^= pk[i];
+    msc += 1e-3f;
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc + __float_as_uint(sum0 + sum1 + sum2 + sum3);
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int CH, int POLY>
+void runp(const char* name, const float* in, uint32_t* out, unsigned long long* cyc) {
+  printf("%-46s", name);
+  const int iters = 2000;
+  for (int threads : {128, 256, 384}) {
+    kp<CH, POLY><<<148, threads>>>(in, out, cyc, 0.18f, 3.0f, iters);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf(" ERR %s", cudaGetErrorString(e)); continue; }
+    unsigned long long h[148];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double avg = 0;
+    for (int i = 0; i < 148; ++i) avg += h[i];
+    avg /= 148;
+    printf("  %dw/smsp: %6.2f cyc/elem/warp (%5.2f per SMSP)", threads / 128, avg / iters / 64, avg / iters / 64 / (threads / 128));
+  }
+  printf("\n");
+}
+
+template <int MODE>
+void run(const char* name, const float* in, uint32_t* out, unsigned long long* cyc) {
+  printf("%-46s", name);
+  const int iters = 2000;
+  for (int threads : {128, 256, 384}) {
+    k<MODE><<<148, threads>>>(in, out, cyc, 0.18f, 3.0f, iters);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf(" ERR %s", cudaGetErrorString(e)); continue; }
+    unsigned long long h[148];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double avg = 0;
+    for (int i = 0; i < 148; ++i) avg += h[i];
+    avg /= 148;
+    printf("  %dw/smsp: %6.2f cyc/elem/warp (%5.2f per SMSP)", threads / 128, avg / iters / 64, avg / iters / 64 / (threads / 128));
+  }
+  printf("\n");
+}
+
+int main() {
+  float* in; uint32_t* out; unsigned long long* cyc;
+  cudaMalloc(&in, 512 * 64 * 4); cudaMemset(in, 0, 512 * 64 * 4);
+  cudaMalloc(&out, 148 * 512 * 4); cudaMalloc(&cyc, 148 * 8);
+  run<0>("ffma + ex2 + fadd + cvt.bf16x2/2", in, out, cyc);
+  run<1>("ffma2 + ex2 + fadd + cvt.bf16x2/2", in, out, cyc);
+  run<2>("ffma + ex2 + fadd (no pack)", in, out, cyc);
+  run<3>("ffma + ex2 + cvt (no fadd)", in, out, cyc);
+  run<4>("ffma + ex2 only", in, out, cyc);
+  run<5>("every 4th exp polynomial", in, out, cyc);
+  runp<8, 0>("pipelined by 8", in, out, cyc);
+  runp<16, 0>("pipelined by 16", in, out, cyc);
+  runp<32, 0>("pipelined by 32", in, out, cyc);
+  runp<16, 4>("pipelined by 16, every 4th polynomial", in, out, cyc);
+  runp<16, 3>("pipelined by 16, every 3rd polynomial", in, out, cyc);
+  runp<32, 4>("pipelined by 32, every 4th polynomial", in, out, cyc);
+  runp<16, 2>("pipelined by 16, every 2nd polynomial", in, out, cyc);
+  return 0;
+}
