@@ -230,7 +230,7 @@ def run_ours(args):
                        "l2": "per-step working set (>6 GB) exceeds the 126 MB L2; no explicit flush",
                        "weights": "seeded random init N(0, 0.02^2)", "sampler_steps_per_video": SAMPLER_STEPS},
             "tensor_frac_of_peak_whole_step": round(FLOP_PER_CFG_STEP_FULL / (ms_per_step * 1e-3) / world / 1e12 / tf_peak, 4),
-            "roofline": {"bound": "tensor", "kernel": "attn3_kernel (tcgen05 flash attention, head_dim 64, four softmax streams)",
+            "roofline": {"bound": "tensor", "kernel": "attn4_kernel (tcgen05 flash attention, head_dim 64: double-buffered scores, 16 softmax warps, Q in TMEM)",
                          "achieved": round(achieved, 1), "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": round(achieved / tf_peak, 4), "traffic": None, "peak_source": how,
                          "launch_ms": round(attn_avg, 4), "launches_timed": len(attn_ms),

@@ -31,6 +31,10 @@ struct AttnParams {
   int heads, nq, nkv;
   float scale_log2;
   int stagger;       // cycles by which query tile 1 starts its softmax after tile 0 (attn2_kernel)
+  const bf16* q;     // [BH, q_rows, 64] (attn4_kernel reads Q rows directly)
+  int q_rows;
+  int* redo;         // [grid] attn4_kernel: 1 = recompute this CTA with the exact kernel
+  int redo_only;     // attn3_kernel: run only the CTAs with redo[cta] != 0
   int trace_cta;     // PROF: CTA whose event trace is recorded
   long long* prof;   // per-(CTA, warp) phase cycle counters (profiling variants only)
 };
@@ -385,7 +389,8 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   uint64_t* s_full = v_empty + kKS2;     // [t][b] = 4
   uint64_t* p_full = s_full + 4;         // [t][b] = 4
   uint64_t* o_done = p_full + 4;         // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* all_done = o_done + 2;       // 1: every MMA of this CTA has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -422,6 +427,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     }
     mbar_init(&o_done[0], 1);
     mbar_init(&o_done[1], 1);
+    mbar_init(all_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -538,6 +544,7 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         }
         if (leader) { LD_TRACE(0, i, 3); }
       }
+      if (leader) umma_commit(all_done);
       if constexpr (PROF) {
         if (leader && p.prof != nullptr) {
           long long* d = p.prof + ((int64_t)blockIdx.x * 12 + 1) * 8;
@@ -663,9 +670,9 @@ attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     }
 
     // epilogue: O / l
-    // the softmax may run up to two PVs ahead of the tensor pipe: pass the phases in order (parity aliasing)
-    if (n_sub >= 2) mbar_wait(&o_done[t], (n_sub - 2) & 1);
-    mbar_wait(&o_done[t], (n_sub - 1) & 1);
+    // the softmax may run up to two PVs ahead of the tensor pipe, so a parity wait on o_done could alias here:
+    // the end of all MMAs has its own single-use barrier
+    mbar_wait(all_done, 0);
     tc_fence_after();
     if constexpr (PROF) {
       if (lane == 0 && p.prof != nullptr) {
@@ -749,6 +756,8 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   uint64_t* o_done = p_full + 4;         // [stream] = 4
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 4);
 
+  // fix-up launch after attn4_kernel: only the CTAs whose fixed reference maximum overflowed are recomputed
+  if (p.redo_only && p.redo[blockIdx.x] == 0) return;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q_blocks = (p.nq + 255) / 256;
@@ -1056,6 +1065,350 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
   if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Fourth-generation kernel: double-buffered 64-key score blocks (attn2) + 16 softmax warps (attn3) + Q in TMEM,
+// and NO per-block row maximum.
+//
+// Two 128-row query tiles per CTA; each tile has two 64-column score buffers in TMEM so S(t,i+2) is issued right
+// after PV(t,i) and the softmax never waits for the tensor pipe.  Each 32-row TMEM quadrant of a tile is served by
+// a PAIR of warps that split the 64 columns of a sub-block (warp h exponentiates columns [32h, 32h+32)), which
+// puts 4 warps with exponentials on every SMSP (the MUFU unit needs >= 3 to saturate, tools/softmax_mix_bench.cu).
+//
+// Reference maximum: floating point is scale-invariant, so the online-softmax reference only has to prevent
+// overflow, not track the running maximum.  Each row takes the maximum of its FIRST sub-block as the reference
+// for the whole row (both warps of a pair load that sub-block entirely, so they agree without communicating) and
+// never rescales: later scores may exceed the reference by up to 2^127 before exp2 overflows, and terms far below
+// it flush to zero exactly as their true weight demands.  That removes the 64 FMNMX + vote + correction logic per
+// row and sub-block.  Overflow (a score more than ~127 log2-units above the first block's maximum — never seen on
+// LayerNormed q/k, but constructible) makes the row sum or the output non-finite; the CTA then raises redo[cta],
+// and a second launch of the exact kernel (attn3_kernel, per-block maxima and rescaling) recomputes only the
+// flagged CTAs.  tests/test_kernels_gpu.py::test_attention_overflow_fixup covers that path.
+//
+// Q is stored once into TMEM (bf16 pairs, one row per lane) by the softmax threads, so S = Q K^T runs as a TS-mode
+// MMA whose only shared-memory operand is the K sub-block: 32 clk per 128x64x16 instead of 48 (tools/mma_bench.cu).
+// P has its own 32-column buffer per tile; a warp waits for PV(t,i-1) before overwriting it.
+//   warps 0-15: softmax (tile w>>3, column half (w>>2)&1, TMEM quadrant w&3)   (16 idle)   warp 17: TMA producer
+//   warps 18, 19: MMA issuers of query tile 0 and 1.  One issuer for both tiles spends ~1900 clk per sub-block in
+//   its serial scalar code (barrier polls, descriptor arithmetic, R2UR) and was the bottleneck; the two tiles are
+//   independent instruction streams for the tensor pipe, so each gets its own issuing warp (K/V ring stages are
+//   released by one commit from each).
+//   TMEM columns: S(t,b) at 64(2t+b) [0,256) ; O_t at 256+64t [256,384) ; Q_t at 384+32t [384,448) ;
+//                 P_t at 448+32t [448,512)
+constexpr int kAttn4Threads = 640;
+constexpr int kKS4 = 4;
+constexpr int kAttn4Smem = 2 * kKS4 * kTileBytes + 2 * 2 * 128 * 4 /* row-sum exchange */ + 1024 + 256;
+
+template <int POLY_EVERY, bool PROF>
+__global__ void __launch_bounds__(kAttn4Threads, 1)
+attn4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+             const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;                                // kKS4 tiles
+  uint8_t* sV = sK + kKS4 * kTileBytes;              // kKS4 tiles
+  float* sL = reinterpret_cast<float*>(sV + kKS4 * kTileBytes);   // [tile][half][128] partial row sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sL + 2 * 2 * 128);
+  uint64_t* q_ready = bars;              // [tile] = 2
+  uint64_t* k_full = bars + 2;           // kKS4
+  uint64_t* k_empty = k_full + kKS4;
+  uint64_t* v_full = k_empty + kKS4;
+  uint64_t* v_empty = v_full + kKS4;
+  uint64_t* s_full = v_empty + kKS4;     // [t][b] = 4
+  uint64_t* p_full = s_full + 4;         // [t][b] = 4
+  uint64_t* o_done = p_full + 4;         // [t] = 2
+  uint64_t* all_done = o_done + 2;       // 1: every MMA of this CTA has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_blocks = (p.nq + 255) / 256;
+  const int bh = blockIdx.x / q_blocks;
+  const int q0 = (blockIdx.x % q_blocks) * 256;
+  const int n_tiles = (p.nkv + 127) / 128;   // TMA boxes
+  const int n_sub = (p.nkv + 63) / 64;       // 64-key sub-blocks
+
+  if (warp == 17 && lane == 0) {
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    for (int s = 0; s < kKS4; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 2);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 2);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 256);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_ready[i], 128);
+      mbar_init(&o_done[i], 1);
+    }
+    mbar_init(all_done, 2);
+    fence_barrier_init();
+  }
+  if (warp == 19) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  bool bad = false;   // softmax threads: non-finite row sum or output (overflow of the fixed reference maximum)
+
+  // The producer and issuer warps run warp-uniform code and issue through an elect.sync leader: ptxas then emits
+  // back-to-back UTMALDG / UTCHMMA instead of a per-instruction divergence loop (measured: ~100 clk -> 32 clk).
+  if (warp >= 16) reg_dealloc<56>();   // releases 4 x 32 x 40 = 5120 registers
+  if (warp == 17) {
+    // ------------------------------------------------------------------ TMA producer
+    const bool leader = elect_one();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&k_empty[s], ph ^ 1);
+      if (leader) {
+        mbar_expect_tx(&k_full[s], kTileBytes);
+        tma_load_3d(sK + s * kTileBytes, &tmap_k, &k_full[s], 0, j * 128, bh);
+      }
+      mbar_wait(&v_empty[s], ph ^ 1);
+      if (leader) {
+        mbar_expect_tx(&v_full[s], kTileBytes);
+        tma_load_3d(sV + s * kTileBytes, &tmap_v, &v_full[s], 0, j * 128, bh);
+      }
+      if (++s == kKS4) { s = 0; ph ^= 1; }
+    }
+  } else if (warp >= 18) {
+    // ------------------------------------------------------------------ MMA issuer of query tile t
+    const int t = warp - 18;
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);  // B (=V) is N-major
+    const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK));
+    const uint64_t vdesc = make_sdesc_sw128(smem_u32(sV));
+    const uint32_t tm_s = tmem_base + 128 * t;        // S(t,0); S(t,1) 64 columns further
+    const uint32_t tm_o = tmem_base + 256 + 64 * t;
+    const uint32_t tm_q = tmem_base + 384 + 32 * t;
+    const uint32_t tm_p = tmem_base + 448 + 32 * t;
+    // descriptor address units are 16 B: ring stage = 1024, 64-row half = 512
+    // S(t, i) = Q_t K_i^T into buffer i&1; Q_t from TMEM (8 columns per 16-dim K step)
+    auto issue_s = [&](int i) {
+      const uint64_t bdesc = kdesc + uint32_t(((i >> 1) % kKS4) * (kTileBytes >> 4) + (i & 1) * (kTileBytes >> 5));
+      const uint32_t d = tm_s + (i & 1) * 64;
+      if (leader) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ts(d, tm_q + 8 * k, bdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[2 * t + (i & 1)]);
+      }
+    };
+    // O_t += P(t,i) V_i ; P: 128 lanes x 64 keys bf16 = the tile's 32-column P buffer
+    auto issue_pv = [&](int i) {
+      const uint64_t bdesc = vdesc + uint32_t(((i >> 1) % kKS4) * (kTileBytes >> 4) + (i & 1) * (kTileBytes >> 5));
+      if (leader) {
+        // 16 keys per step: 16 rows x 128 B = 2048 B (encoded 128)
+        umma_ts(tm_o, tm_p, bdesc, idesc_o, i != 0);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) umma_ts(tm_o, tm_p + k * 8, bdesc + 128 * k, idesc_o, 1u);
+        umma_commit(&o_done[t]);
+      }
+    };
+    auto k_wait = [&](int tile) { mbar_wait(&k_full[tile % kKS4], (tile / kKS4) & 1); };
+    auto v_wait = [&](int tile) { mbar_wait(&v_full[tile % kKS4], (tile / kKS4) & 1); };
+
+    mbar_wait(&q_ready[t], 0);
+    k_wait(0);
+    tc_fence_after();
+    issue_s(0);
+    if (n_sub > 1) issue_s(1);
+    if (leader) umma_commit(&k_empty[0]);
+    long long w_kv = 0, w_p0 = 0, t_all = 0, w_ipv = 0, w_is = 0;
+    if constexpr (PROF) t_all = clock64();
+    for (int i = 0; i < n_sub; ++i) {
+      const int b = i & 1;
+      const bool has_next = (i + 2) < n_sub;
+      long long c0 = 0;
+      if constexpr (PROF) c0 = clock64();
+      if (b == 0) v_wait(i >> 1);
+      if (has_next && b == 0) k_wait((i + 2) >> 1);
+      if constexpr (PROF) { const long long c1 = clock64(); w_kv += c1 - c0; c0 = c1; }
+      mbar_wait(&p_full[2 * t + b], (i >> 1) & 1);
+      if constexpr (PROF) { const long long c1 = clock64(); w_p0 += c1 - c0; c0 = c1; }
+      tc_fence_after();
+      issue_pv(i);
+      if constexpr (PROF) { const long long c1 = clock64(); w_ipv += c1 - c0; c0 = c1; }
+      if (leader && (b == 1 || i == n_sub - 1)) umma_commit(&v_empty[(i >> 1) % kKS4]);
+      if (has_next) {
+        issue_s(i + 2);
+        if (leader && (b == 1 || i + 2 == n_sub - 1)) umma_commit(&k_empty[((i + 2) >> 1) % kKS4]);
+      }
+      if constexpr (PROF) w_is += clock64() - c0;
+    }
+    if (leader) umma_commit(all_done);
+    if constexpr (PROF) {
+      if (leader && p.prof != nullptr) {
+        long long* d = p.prof + ((int64_t)blockIdx.x * 20 + warp) * 8;
+        d[0] = w_kv; d[1] = w_p0; d[2] = 0; d[3] = clock64() - t_all; d[4] = w_ipv; d[5] = w_is;
+      }
+    }
+  } else if (warp < 16) {
+    reg_alloc<104>();   // 16 warps x 32 x 8 = 4096 <= the 5120 registers released by the control warpgroup
+    // -------------------------------------------------------------------- softmax / correction / epilogue
+    const int t = warp >> 3;                    // query tile
+    const int h = (warp >> 2) & 1;              // column half of every sub-block exponentiated by this warp
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    const int q_row = q0 + t * 128 + row_in_tile;
+    const uint32_t lane_base = uint32_t(quad * 32) << 16;
+    const uint32_t ts = tmem_base + lane_base + t * 128;         // S(t,0); S(t,1) is 64 columns further
+    const uint32_t to = tmem_base + lane_base + 256 + t * 64;    // O_t
+    const float sl2 = p.scale_log2;
+
+    if (h == 0) {
+      // Q row -> TMEM (bf16 pairs: column c holds dims 2c, 2c+1), zero beyond nq
+      uint32_t qr[32];
+      if (q_row < p.nq) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.q + ((int64_t)bh * p.q_rows + q_row) * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = __ldg(src + c);
+          qr[4 * c] = v.x; qr[4 * c + 1] = v.y; qr[4 * c + 2] = v.z; qr[4 * c + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) qr[c] = 0u;
+      }
+      LD_TMEM_ST32(tmem_base + lane_base + 384 + 32 * t, qr);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&q_ready[t]);
+    }
+
+    float msc = 0.f;   // reference maximum of the row (first sub-block) * scale_log2
+    float l = 0.f;
+    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+    long long tp = 0;
+    if constexpr (PROF) tp = clock64();
+    const uint32_t tp_addr = tmem_base + lane_base + 448 + 32 * t + 16 * h;
+    bool s_ready = false;   // s_full(i) already observed complete by the probe of the previous iteration
+    for (int i = 0; i < n_sub; ++i) {
+      const int b = i & 1;
+      const uint32_t tsb = ts + b * 64;
+      if (!s_ready) mbar_wait(&s_full[2 * t + b], (i >> 1) & 1);
+      tc_fence_after();
+      LD_PROF(0);
+      uint32_t s[32];   // this warp's column half
+      LD_TMEM_LD32(tsb + 32 * h, s);
+      const int valid = p.nkv - i * 64 - 32 * h;
+      if (i == 0) {
+        // reference maximum of the row = maximum of the whole first sub-block (identical in both warps of the pair)
+        uint32_t so[32];
+        LD_TMEM_LD32(tsb + 32 * (h ^ 1), so);
+        tmem_ld_wait();
+        const int valid_o = p.nkv - 32 * (h ^ 1);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c < valid) mx = fmaxf(mx, __uint_as_float(s[c]));
+          if (c < valid_o) mx = fmaxf(mx, __uint_as_float(so[c]));
+        }
+        msc = mx * sl2;
+      } else {
+        tmem_ld_wait();
+      }
+      LD_PROF(1);
+      if (valid < 32) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c >= valid) s[c] = 0xff800000u;  // -inf
+      }
+      LD_PROF(2);
+      // Probe the two barriers the end of this iteration and the start of the next one depend on now, so their
+      // ~100-clk round trips overlap the exponentials (both are almost always complete already).
+      const bool pv_done = (i == 0) || mbar_test_wait(&o_done[t], (i - 1) & 1);
+      s_ready = (i + 1 < n_sub) && mbar_test_wait(&s_full[2 * t + (b ^ 1)], ((i + 1) >> 1) & 1);
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      uint32_t pk[16];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float pv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int idx = 4 * c + e;
+          const float x = fmaf(__uint_as_float(s[idx]), sl2, -msc);
+          if constexpr (POLY_EVERY > 0) {
+            pv[e] = ((idx % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x) : ex2(x);
+          } else {
+            pv[e] = ex2(x);
+          }
+        }
+        sum0 += pv[0];
+        sum1 += pv[1];
+        sum2 += pv[2];
+        sum3 += pv[3];
+        pk[2 * c] = pack_bf16x2(pv[0], pv[1]);
+        pk[2 * c + 1] = pack_bf16x2(pv[2], pv[3]);
+      }
+      l += (sum0 + sum1) + (sum2 + sum3);
+      LD_PROF(3);
+      if (!pv_done) mbar_wait(&o_done[t], (i - 1) & 1);   // PV(t,i-1) has consumed the P buffer
+      LD_TMEM_ST16(tp_addr, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[2 * t + b]);
+      LD_PROF(4);
+    }
+
+    // ---- epilogue: total row sum = the two halves' partial sums (same reference maximum); warp h writes output
+    //      columns [32h, 32h+32) of the head.  The softmax may run up to two PVs ahead of the tensor pipe, so a
+    //      parity wait on o_done could alias here (both last phases may already have completed): the end of all
+    //      MMAs has its own single-use barrier.
+    mbar_wait(all_done, 0);
+    tc_fence_after();
+    if constexpr (PROF) {
+      if (lane == 0 && p.prof != nullptr) {
+        long long* d = p.prof + ((int64_t)blockIdx.x * 20 + warp) * 8;
+        for (int e = 0; e < 6; ++e) d[e] = prof_acc[e];
+      }
+    }
+    sL[(t * 2 + h) * 128 + row_in_tile] = l;
+    named_bar_sync(1 + t, 256);     // the 8 warps of query tile t
+    const float l_all = l + sL[(t * 2 + (h ^ 1)) * 128 + row_in_tile];
+    const float inv_l = 1.0f / l_all;
+    const bool valid_row = q_row < p.nq;
+    const int bb = bh / p.heads, hd = bh - bb * p.heads;
+    const int c0 = 32 * h;
+    uint32_t o[32];
+    LD_TMEM_LD32(to + c0, o);
+    tmem_ld_wait();
+    if (valid_row) {
+      bad = !(l_all < INFINITY) || !(l_all > 0.f);   // inf / NaN row sum (or everything flushed to zero)
+      bf16* orow = p.out + ((int64_t)bb * p.nq + q_row) * (p.heads * 64) + hd * 64 + c0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          f[e] = __uint_as_float(o[g * 8 + e]) * inv_l;
+          bad |= !(fabsf(f[e]) < INFINITY);
+        }
+        uint4 v;
+        v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+        v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+        *reinterpret_cast<uint4*>(orow + g * 8) = v;
+        if (p.out_f32 != nullptr) {
+          float* of = p.out_f32 + ((int64_t)bh * p.nq + q_row) * 64 + c0 + g * 8;
+          *reinterpret_cast<float4*>(of) = make_float4(f[0], f[1], f[2], f[3]);
+          *reinterpret_cast<float4*>(of + 4) = make_float4(f[4], f[5], f[6], f[7]);
+        }
+      }
+      if (h == 0 && p.lse != nullptr) p.lse[(int64_t)bh * p.nq + q_row] = msc + log2f(l_all);
+    }
+  }
+
+  tc_fence_before();
+  const int any_bad = __syncthreads_or(bad ? 1 : 0);
+  if (threadIdx.x == 0) p.redo[blockIdx.x] = any_bad;   // 1: the exact kernel recomputes this CTA's 256 rows
+  if (warp == 19) tmem_dealloc<512>(tmem_base);
+}
+
 // (o_acc, lse_acc) <- merge with (o_new, lse_new); log2-domain LSE
 __global__ void __launch_bounds__(256) attn_merge_kernel(float* __restrict__ o_acc, float* __restrict__ lse_acc,
                                                          const float* __restrict__ o_new,
@@ -1131,9 +1484,39 @@ static int launch_attn3(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
   return LD_OK;
 }
 
+template <int POLY_EVERY, bool PROF = false>
+static int launch_attn4(const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& prm, int grid,
+                        cudaStream_t st) {
+  auto kern = attn4_kernel<POLY_EVERY, PROF>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn4Smem));
+    attr_set = true;
+  }
+  kern<<<grid, kAttn4Threads, kAttn4Smem, st>>>(tk, tv, prm);
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}
+
 }  // namespace ld
 
 using namespace ld;
+
+// redo flags of the attn4 + fix-up pair: one int per CTA, grown on demand (allocation only on first use / growth)
+static int* g_redo = nullptr;
+static int g_redo_cap = 0;
+static int redo_buffer(int grid, int** out) {
+  if (grid > g_redo_cap) {
+    if (g_redo != nullptr) LD_CHECK_CUDA(cudaFree(g_redo));
+    g_redo = nullptr;
+    g_redo_cap = 0;
+    const int cap = grid + grid / 2 + 1024;
+    LD_CHECK_CUDA(cudaMalloc(&g_redo, sizeof(int) * (size_t)cap));
+    g_redo_cap = cap;
+  }
+  *out = g_redo;
+  return LD_OK;
+}
 
 static long long* g_attn_prof = nullptr;
 // Debug hook (tools/attn_phase_prof.py): per-(CTA, warp) phase cycle counters for the next ld_attention_bf16 calls.
@@ -1175,6 +1558,10 @@ extern "C" int ld_attention_bf16(const void* q, const void* k, const void* v, vo
   prm.nkv = nkv;
   prm.prof = nullptr;
   prm.trace_cta = 0;
+  prm.redo = nullptr;
+  prm.redo_only = 0;
+  prm.q = (const bf16*)q;
+  prm.q_rows = q_rows;
   {
     static int stagger = -1;
     if (stagger < 0) {
@@ -1217,6 +1604,28 @@ extern "C" int ld_attention_bf16(const void* q, const void* k, const void* v, vo
     case 33: return launch_attn3<4>(tq, tk, tv, prm, grid, st);
     case 34: return launch_attn3<3>(tq, tk, tv, prm, grid, st);
     case 35: return launch_attn3<2>(tq, tk, tv, prm, grid, st);
+    // fourth-generation kernel (double-buffered scores + column-split warp pairs + Q in TMEM): 48 all MUFU,
+    // 49/50 every 4th/3rd polynomial
+    case 48:
+    case 49:
+    case 50: {
+      rc = redo_buffer(grid, &prm.redo);
+      if (rc != LD_OK) return rc;
+      if (variant == 48 && g_attn_prof != nullptr) {
+        prm.prof = g_attn_prof;
+        rc = launch_attn4<0, true>(tk, tv, prm, grid, st);
+      } else if (variant == 48) {
+        rc = launch_attn4<0>(tk, tv, prm, grid, st);
+      } else if (variant == 49) {
+        rc = launch_attn4<4>(tk, tv, prm, grid, st);
+      } else {
+        rc = launch_attn4<3>(tk, tv, prm, grid, st);
+      }
+      if (rc != LD_OK) return rc;
+      prm.prof = nullptr;
+      prm.redo_only = 1;   // exact kernel, flagged CTAs only (all others exit at once)
+      return launch_attn3<0>(tq, tk, tv, prm, grid, st);
+    }
     default:
       set_error("ld_attention_bf16: unknown variant %d", variant);
       return LD_ERR_ARG;

@@ -3,6 +3,7 @@
 // the bit layouts follow the PTX ISA "tcgen05 matrix / instruction descriptor" tables.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_bf16.h>
 
 namespace ld {
@@ -45,10 +46,40 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a while when the phase is still pending)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+#ifdef LD_HANG_CHECK
+// Debug build (LD_EXTRA_NVCC_FLAGS=-DLD_HANG_CHECK): a wait that polls ~2^24 times reports itself and traps.
+static __device__ __noinline__ void mbar_hang_report(uint32_t bar_addr, uint32_t parity, bool fatal) {
+  if ((threadIdx.x & 31) == 0 || fatal)
+    printf("HANG%s block %d warp %d lane %d: mbarrier smem 0x%x parity %u\n", fatal ? " (trap)" : "", blockIdx.x,
+           threadIdx.x >> 5, threadIdx.x & 31, bar_addr, parity);
+  if (fatal) __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    ++polls;
+    if (polls == (1u << 21)) mbar_hang_report(smem_u32(bar), parity, false);
+    if (polls > (1u << 23)) mbar_hang_report(smem_u32(bar), parity, true);
+  }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+#endif
 
 // generic-proxy smem writes -> visible to the async proxy (TMA store / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -186,6 +217,12 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr) {
 #define LD_TMEM_ST8(taddr, r)                                                                                   \
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), \
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])                       \
+               : "memory")
+
+#define LD_TMEM_ST16(taddr, r)                                                                                 \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), \
+               "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])   \
                : "memory")
 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

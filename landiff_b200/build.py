@@ -21,7 +21,7 @@ SOURCES = ["abi.cu", "gemm_tcgen05.cu", "attn_tcgen05.cu", "row_kernels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + os.environ.get("LD_EXTRA_NVCC_FLAGS", "").split()   # e.g. -DLD_HANG_CHECK for the mbarrier watchdog build
 
 
 def _nvcc() -> str:

@@ -96,7 +96,7 @@ def test_gemm_all_epilogues():
     report("gemm UNPATCHIFY", out, y.permute(0, 1, 4, 2, 5, 3, 6).reshape(B, T, Cc, 2 * Hp, 2 * Wp))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 4, 6, 16, 17, 18, 19, 32, 33, 34, 35])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 6, 16, 17, 18, 19, 32, 33, 34, 35, 48, 49, 50])
 def test_attention(variant):
     torch.manual_seed(1)
     for (B, H, nq, nkv) in [(1, 1, 128, 128), (1, 1, 256, 128), (1, 2, 300, 300), (2, 3, 886, 886), (1, 2, 500, 1000),
@@ -114,6 +114,31 @@ def test_attention(variant):
         lse_ref = torch.logsumexp(s, -1) * 1.4426950408889634
         report("   lse", lse, lse_ref.view(B * H, nq), 1e-5)
         report("   out_f32", of, ref.reshape(B * H, nq, 64))
+
+
+@pytest.mark.parametrize("variant", [48, 32, 0])
+def test_attention_overflow_fixup(variant):
+    """One late key whose score is hundreds of log2-units above every row's first-block maximum: the fixed reference
+    maximum of attn4_kernel overflows, the CTA raises its redo flag and the exact kernel recomputes it.  Rows with a
+    negative projection on that key never overflow (mixed flagged / unflagged CTAs)."""
+    torch.manual_seed(5)
+    B, H, nq, nkv = 1, 2, 1000, 3000
+    q = torch.randn(B, H, nq, 64, device=dev)
+    k = torch.randn(B, H, nkv, 64, device=dev)
+    v = torch.randn(B, H, nkv, 64, device=dev)
+    q[:, 0, :, 0] = q[:, 0, :, 0].abs() + 3.0          # head 0: every row overflows
+    q[:, 1, :300, 0] = -(q[:, 1, :300, 0].abs() + 3.0)  # head 1: first 300 rows never do, the rest do
+    q[:, 1, 300:, 0] = q[:, 1, 300:, 0].abs() + 3.0
+    k[:, :, 2500, :] = 0
+    k[:, :, 2500, 0] = 400.0
+    q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    lse = torch.zeros(B * H, nq, device=dev)
+    out = ops.attention(q, k, v, variant=variant, lse=lse)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    report(f"attn overflow v{variant}", out, ref.permute(0, 2, 1, 3).reshape(B, nq, H * 64))
+    s = (q.float() @ k.float().transpose(-1, -2)) * 0.125
+    report("   lse", lse, (torch.logsumexp(s, -1) * 1.4426950408889634).view(B * H, nq), 1e-5)
 
 
 def test_row_kernels():

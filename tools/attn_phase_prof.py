@@ -15,7 +15,7 @@ out = torch.empty(B, N, H * 64, device=dev, dtype=torch.bfloat16)
 grid = B * H * ((N + 255) // 256)
 VAR = int(os.environ.get("LD_ATTN_VARIANT", "32"))
 NW = 20 if VAR >= 32 else 12
-FIRST = 4
+FIRST, LAST, MMAW = (0, 16, 19) if VAR >= 48 else (4, NW, 1)
 prof_all = torch.zeros(grid * NW * 8 + 3 * 64 * 8, device=dev, dtype=torch.int64)
 prof = prof_all[:grid * NW * 8].view(grid, NW, 8)
 lib = _C.load()
@@ -28,13 +28,14 @@ ops.attention(q, k, v, out=out, variant=VAR)
 torch.cuda.synchronize()
 lib.ld_debug_attn_prof(None)
 n_sub = (N + 63) // 64
-per_warp = n_sub if VAR < 32 else n_sub / 2
+per_warp = n_sub if (VAR < 32 or VAR >= 48) else n_sub / 2
 p = prof.double().cpu()
-sm = p[:, FIRST:NW, :5].mean(dim=(0, 1)) / per_warp
+sm = p[:, FIRST:LAST, :5].mean(dim=(0, 1)) / per_warp
 names = ["wait s_full", "tcgen05.ld", "mask+max+rescale", "exp+sum+pack", "st+fence+arrive"]
 print(f"variant {VAR} N={N} n_sub={n_sub}: softmax warp cycles per 64-key sub-block it processes (mean over CTAs and warps)")
 for n, c in zip(names, sm.tolist()):
     print(f"  {n:20s} {c:8.1f}")
 print(f"  {'total':20s} {sm.sum().item():8.1f}")
-mm = p[:, 1, :4].mean(dim=0) / n_sub
-print("MMA issuer per sub-block (both tiles): wait k/v %.1f  wait p_full[tile 0] %.1f  wait p_full[tile 1] %.1f  loop total %.1f" % tuple(mm.tolist()))
+for w in ((18, 19) if VAR >= 48 else (MMAW,)):
+    mm = p[:, w, :6].mean(dim=0) / n_sub
+    print("MMA issuer warp %d per sub-block: wait k/v %.1f  wait p_full %.1f  (%.1f)  loop total %.1f  issue PV %.1f  issue S %.1f" % ((w,) + tuple(mm.tolist())))

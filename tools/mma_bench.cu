@@ -9,6 +9,7 @@
 using namespace ld;
 
 // MODE 0: SS only; 1: TS only (B N-major); 2: attention pattern: 4 x SS(N=64) then 4 x TS(N=64) alternating
+// MODE 3: TS with K-major B; 4: attn4 pattern: 4 x TS(K-major B) then 4 x TS(N-major B)
 template <int N, int MODE, int NACC, int COMMIT_EVERY>
 __global__ void __launch_bounds__(128, 1) k(long long* out, int total) {
   extern __shared__ uint8_t smem_raw[];
@@ -30,11 +31,13 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int total) {
     for (int i = 0; i < total; i += 4) {
       const int g = i / 4;
       const uint32_t d = tm + (g % NACC) * N;
-      const bool ts = MODE == 1 || (MODE == 2 && (g & 1));
+      const bool ts = MODE == 1 || (MODE == 2 && (g & 1)) || (MODE == 4 && (g & 1));
+      const bool tsk = MODE == 3 || (MODE == 4 && !(g & 1));
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-          if (ts) umma_ts(d, tm + 448 + ks * 8, bdesc + 128 * ks, idesc_ts, 1);
+          if (tsk) umma_ts(d, tm + 416 + ks * 8, bdesc + 2 * ks, idesc_ss, 1);
+          else if (ts) umma_ts(d, tm + 448 + ks * 8, bdesc + 128 * ks, idesc_ts, 1);
           else umma_ss(d, adesc + 2 * ks, bdesc + 2 * ks, idesc_ss, 1);
         }
         if (COMMIT_EVERY && (g % COMMIT_EVERY) == COMMIT_EVERY - 1) umma_commit(&bar[1]);
@@ -55,7 +58,7 @@ void run(long long* out) {
   const int total = 1024;
   auto kern = k<N, MODE, NACC, COMMIT_EVERY>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  printf("N=%3d %-4s acc=%d commit/%d groups |", N, MODE == 0 ? "SS" : MODE == 1 ? "TS" : "S+TS", NACC, COMMIT_EVERY);
+  printf("N=%3d %-4s acc=%d commit/%d groups |", N, MODE == 0 ? "SS" : MODE == 1 ? "TS" : MODE == 2 ? "S+TS" : MODE == 3 ? "TSk" : "TSk+TS", NACC, COMMIT_EVERY);
   for (int grid : {148, 1}) {
     kern<<<grid, 128, 100 * 1024>>>(out, total);
     cudaError_t e = cudaDeviceSynchronize();
@@ -81,5 +84,6 @@ int main() {
   run<64, 2, 1, 0>(out);  run<64, 2, 2, 0>(out);  run<64, 2, 4, 0>(out);
   run<64, 0, 2, 1>(out);  run<64, 2, 4, 1>(out);  run<128, 0, 2, 1>(out); run<192, 0, 2, 4>(out);
   run<32, 0, 2, 0>(out);  run<16, 0, 2, 0>(out);
+  run<64, 3, 1, 0>(out);  run<64, 3, 2, 0>(out);  run<128, 3, 2, 0>(out);  run<64, 4, 4, 1>(out);
   return 0;
 }
