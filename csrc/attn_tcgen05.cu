@@ -1,14 +1,15 @@
 // Full (non-causal) self-attention for head_dim 64 on sm_100a: flash-style online softmax with both
-// contractions on tcgen05 tensor cores and S / P / O resident in TMEM.
+// contractions on tcgen05 tensor cores and Q / S / P / O resident in TMEM.  Replaces
+// F.scaled_dot_product_attention as reached from dit_video_concat.py:655-664 (SAT attention_fn_default).
 //
-// One CTA owns 256 query rows of one (sample, head) as two 128-row tiles that ping-pong on the tensor pipe:
-//   warp 0        TMA producer: Q once, then K_j / V_j 128x64 boxes through KS-deep mbarrier rings
-//   warp 1        tcgen05.mma issuer (one thread):  S_t = Q_t K_j^T  (128x128x64, SS),
-//                                                   O_t += P_t V_j   (128x64x128, P from TMEM or smem; V N-major)
-//   warps 4-7     softmax for tile 0 (one thread per query row: tcgen05.ld S row -> max / exp2 / sum ->
-//   warps 8-11    softmax for tile 1   bf16 P -> tcgen05.st over S (or swizzled smem) ; lazy O rescale ; epilogue)
-// The softmax of tile t overlaps the MMAs of tile 1-t.  K/V tail columns are masked to -inf; TMA zero-fills
-// out-of-range rows.  Replaces F.scaled_dot_product_attention as reached from dit_video_concat.py:655-664.
+// Two kernels (history and measurements: DESIGN.md section 3a):
+//   attn4_kernel   the product path: per CTA 256 query rows as two 128-row tiles, double-buffered 64-key score
+//                  blocks, 16 softmax warps in column-split pairs, Q in TMEM (TS-mode S = Q K^T), two MMA issuer
+//                  warps, one fixed reference maximum per row (first sub-block) with overflow detection.
+//   attn3_kernel   the exact kernel (per-block maxima, lazy rescaling, four independent softmax streams); launched
+//                  after attn4_kernel to recompute only the CTAs that flagged an overflow, and on its own as
+//                  variant 1.
+// K/V tail columns are masked to -inf; TMA zero-fills out-of-range rows.
 #include <cstdlib>
 #include "host_util.h"
 #include "ptx.cuh"
@@ -17,12 +18,8 @@ namespace ld {
 
 using bf16 = __nv_bfloat16;
 
-constexpr int kAttnThreads = 384;
-constexpr int kKS = 3;                       // K/V ring depth
 constexpr int kTileBytes = 128 * 64 * 2;     // 16 KB: one 128x64 bf16 box
-constexpr int kPBytes = 128 * 128 * 2;       // 32 KB: one P tile in smem (variant 1)
-constexpr int kAttnSmem = 2 * kTileBytes + 2 * kKS * kTileBytes + 2 * kPBytes + 1024 + 256;
-constexpr float kRescaleThreshold = 8.0f;    // log2 units
+constexpr float kRescaleThreshold = 8.0f;    // log2 units (attn3_kernel's lazy rescaling)
 
 struct AttnParams {
   bf16* out;        // [B, nq, heads*64]
@@ -30,12 +27,10 @@ struct AttnParams {
   float* out_f32;   // [BH, nq, 64] or null
   int heads, nq, nkv;
   float scale_log2;
-  int stagger;       // cycles by which query tile 1 starts its softmax after tile 0 (attn2_kernel)
   const bf16* q;     // [BH, q_rows, 64] (attn4_kernel reads Q rows directly)
   int q_rows;
   int* redo;         // [grid] attn4_kernel: 1 = recompute this CTA with the exact kernel
   int redo_only;     // attn3_kernel: run only the CTAs with redo[cta] != 0
-  int trace_cta;     // PROF: CTA whose event trace is recorded
   long long* prof;   // per-(CTA, warp) phase cycle counters (profiling variants only)
 };
 
@@ -45,11 +40,12 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// 2^x for x <= ~8 on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial, max rel. error
-// 8.8e-5 — far below the bf16 rounding of P): floor via round-down magic add, fraction in [0,1), exponent
-// re-inserted by an integer add.  Offloads part of the softmax exponentials from the 16-op/clk MUFU unit.
+// 2^x on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial, max rel. error 8.8e-5 — far
+// below the bf16 rounding of P): floor via round-down magic add, fraction in [0,1), exponent re-inserted by an
+// integer add.  Offloads part of the softmax exponentials from the 16-op/clk MUFU unit.  x >= 128 yields a NaN
+// bit pattern (exponent field 255), which attn4_kernel's overflow detection catches like MUFU's +inf.
 __device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -127.0f);
+  x = fminf(fmaxf(x, -127.0f), 128.0f);
   float xr;
   asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(xr) : "f"(x), "f"(12582912.0f));  // 1.5 * 2^23: low mantissa bits = floor(x)
   const float f = x - (xr - 12582912.0f);
@@ -60,661 +56,13 @@ __device__ __forceinline__ float ex2_poly(float x) {
 }
 
 // POLY_EVERY = n > 0: every n-th exponential of a row goes to ex2_poly, the others to MUFU.EX2; 0: all MUFU.
-template <bool P_IN_TMEM, int POLY_EVERY>
-__global__ void __launch_bounds__(kAttnThreads, 1)
-attn_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-            const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                // 2 tiles
-  uint8_t* sK = sQ + 2 * kTileBytes;                 // kKS tiles
-  uint8_t* sV = sK + kKS * kTileBytes;               // kKS tiles
-  uint8_t* sP = sV + kKS * kTileBytes;               // 2 x 32 KB (variant 1 only)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
-  uint64_t* q_full = bars;               // 1
-  uint64_t* k_full = bars + 1;           // kKS
-  uint64_t* k_empty = k_full + kKS;
-  uint64_t* v_full = k_empty + kKS;
-  uint64_t* v_empty = v_full + kKS;
-  uint64_t* s_full = v_empty + kKS;      // 2
-  uint64_t* p_full = s_full + 2;         // 2
-  uint64_t* o_done = p_full + 2;         // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q_blocks = (p.nq + 255) / 256;
-  const int bh = blockIdx.x / q_blocks;
-  const int q0 = (blockIdx.x % q_blocks) * 256;
-  const int n_tiles = (p.nkv + 127) / 128;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < kKS; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
-    }
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], 128);
-      mbar_init(&o_done[t], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384); P_t aliases the first 64 columns of S_t
-
-  if (warp < 4) {
-    reg_dealloc<56>();
-    // warp-uniform code + elect.sync leader: back-to-back UTMALDG / UTCHMMA (see attn2_kernel)
-    if (warp == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      const bool leader = elect_one();
-      if (leader) {
-        mbar_expect_tx(q_full, 2 * kTileBytes);
-        tma_load_3d(sQ, &tmap_q, q_full, 0, q0, bh);
-        tma_load_3d(sQ + kTileBytes, &tmap_q, q_full, 0, q0 + 128, bh);
-      }
-      int s = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(&k_empty[s], ph ^ 1);
-        if (leader) {
-          mbar_expect_tx(&k_full[s], kTileBytes);
-          tma_load_3d(sK + s * kTileBytes, &tmap_k, &k_full[s], 0, j * 128, bh);
-        }
-        mbar_wait(&v_empty[s], ph ^ 1);
-        if (leader) {
-          mbar_expect_tx(&v_full[s], kTileBytes);
-          tma_load_3d(sV + s * kTileBytes, &tmap_v, &v_full[s], 0, j * 128, bh);
-        }
-        if (++s == kKS) { s = 0; ph ^= 1; }
-      }
-    } else if (warp == 1) {
-      // ---------------------------------------------------------------- MMA issuer
-      const bool leader = elect_one();
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);  // B (=V) is N-major
-      const uint64_t qdesc = make_sdesc_sw128(smem_u32(sQ));
-      const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK));
-      const uint64_t vdesc = make_sdesc_sw128(smem_u32(sV));
-      const uint64_t pdesc = make_sdesc_sw128(smem_u32(sP));
-      auto issue_s = [&](int t, int stage) {
-        const uint64_t adesc = qdesc + uint32_t(t * (kTileBytes >> 4));
-        const uint64_t bdesc = kdesc + uint32_t(stage * (kTileBytes >> 4));
-        if (leader) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(tmem_base + t * 128, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(&s_full[t]);
-        }
-      };
-      auto issue_pv = [&](int t, int stage, bool first) {
-        const uint64_t bdesc = vdesc + uint32_t(stage * (kTileBytes >> 4));
-        const uint32_t d = tmem_base + 256 + t * 64;
-        if (leader) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint32_t acc = (first && k == 0) ? 0u : 1u;
-            // 16 keys per step: V rows advance 16*128 B = 2048 B (encoded 128)
-            if constexpr (P_IN_TMEM) {
-              umma_ts(d, tmem_base + t * 128 + k * 8, bdesc + 128 * k, idesc_o, acc);
-            } else {
-              const uint64_t adesc = pdesc + uint32_t(t * (kPBytes >> 4) + (k >> 2) * (kTileBytes >> 4) + 2 * (k & 3));
-              umma_ss(d, adesc, bdesc + 128 * k, idesc_o, acc);
-            }
-          }
-          umma_commit(&o_done[t]);
-        }
-      };
-
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      if (leader) umma_commit(&k_empty[0]);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < n_tiles; ++j) {
-        int sn = s + 1;
-        uint32_t phn = ph;
-        if (sn == kKS) { sn = 0; phn ^= 1; }
-        const bool has_next = (j + 1) < n_tiles;
-        const uint32_t jpar = j & 1;
-        // tile 0
-        mbar_wait(&p_full[0], jpar);
-        mbar_wait(&v_full[s], ph);
-        tc_fence_after();
-        issue_pv(0, s, j == 0);
-        if (has_next) {
-          mbar_wait(&k_full[sn], phn);
-          tc_fence_after();
-          issue_s(0, sn);
-        }
-        // tile 1
-        mbar_wait(&p_full[1], jpar);
-        tc_fence_after();
-        issue_pv(1, s, j == 0);
-        if (leader) umma_commit(&v_empty[s]);
-        if (has_next) {
-          issue_s(1, sn);
-          if (leader) umma_commit(&k_empty[sn]);
-        }
-        s = sn;
-        ph = phn;
-      }
-    }
-  } else {
-    reg_alloc<208>();
-    // ------------------------------------------------------------------ softmax / correction / epilogue
-    const int t = (warp - 4) >> 2;        // query tile 0/1
-    const int quad = warp & 3;
-    const int row_in_tile = quad * 32 + lane;
-    const int q_row = q0 + t * 128 + row_in_tile;
-    const uint32_t lane_base = uint32_t(quad * 32) << 16;
-    const uint32_t ts = tmem_base + lane_base + t * 128;       // S_t (and P_t)
-    const uint32_t to = tmem_base + lane_base + 256 + t * 64;  // O_t
-    uint8_t* sPt = sP + t * kPBytes;
-    const float sl2 = p.scale_log2;
-
-    float m_used = -INFINITY;  // raw-score units
-    float l = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(&s_full[t], j & 1);
-      tc_fence_after();
-      uint32_t s[128];
-      LD_TMEM_LD32(ts + 0, (s + 0));
-      LD_TMEM_LD32(ts + 32, (s + 32));
-      LD_TMEM_LD32(ts + 64, (s + 64));
-      LD_TMEM_LD32(ts + 96, (s + 96));
-      tmem_ld_wait();
-      const int valid = p.nkv - j * 128;
-      if (valid < 128) {
-#pragma unroll
-        for (int i = 0; i < 128; ++i)
-          if (i >= valid) s[i] = 0xff800000u;  // -inf
-      }
-      float mx4[4] = {__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]), __uint_as_float(s[3])};
-#pragma unroll
-      for (int i = 4; i < 128; i += 4) {  // four independent chains (the compiler fuses pairs into FMNMX3)
-        mx4[0] = fmaxf(mx4[0], __uint_as_float(s[i]));
-        mx4[1] = fmaxf(mx4[1], __uint_as_float(s[i + 1]));
-        mx4[2] = fmaxf(mx4[2], __uint_as_float(s[i + 2]));
-        mx4[3] = fmaxf(mx4[3], __uint_as_float(s[i + 3]));
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-
-      bool need = (j > 0) && ((mx - m_used) * sl2 > kRescaleThreshold);
-      if (j == 0) m_used = mx;
-      if (__any_sync(0xffffffffu, need)) {
-        // lazy correction: bring O_t and l to the new reference maximum (whole warp, tcgen05.ld/st are collective)
-        const float m_new = fmaxf(m_used, mx);
-        const float alpha = ex2((m_used - m_new) * sl2);
-        mbar_wait(&o_done[t], (j - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 64; c += 32) {
-          uint32_t o[32];
-          LD_TMEM_LD32(to + c, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          LD_TMEM_ST32(to + c, o);
-        }
-        l *= alpha;
-        m_used = m_new;
-      }
-      const float msc = m_used * sl2;
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-      uint32_t pk[64];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float pv[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int idx = 4 * i + e;
-          const float x = fmaf(__uint_as_float(s[idx]), sl2, -msc);
-          if constexpr (POLY_EVERY > 0) {
-            pv[e] = ((idx % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x) : ex2(x);
-          } else {
-            pv[e] = ex2(x);
-          }
-        }
-        sum0 += pv[0];
-        sum1 += pv[1];
-        sum2 += pv[2];
-        sum3 += pv[3];
-        pk[2 * i] = pack_bf16x2(pv[0], pv[1]);
-        pk[2 * i + 1] = pack_bf16x2(pv[2], pv[3]);
-      }
-      l += (sum0 + sum1) + (sum2 + sum3);
-      if constexpr (P_IN_TMEM) {
-        LD_TMEM_ST32(ts + 0, (pk + 0));
-        LD_TMEM_ST32(ts + 32, (pk + 32));
-        tmem_st_wait();
-        tc_fence_before();
-      } else {
-        if (j > 0) mbar_wait(&o_done[t], (j - 1) & 1);  // P_t smem still being read by PV_t(j-1)
-        tmem_st_wait();
-        // row r of panel kp (64 keys) lives at kp*16KB + r*128 B, 16-byte chunk c stored at (c ^ (r & 7))
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const int kp = c >> 3, cc = c & 7;
-          uint4 v = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-          *reinterpret_cast<uint4*>(sPt + kp * kTileBytes + row_in_tile * 128 + ((cc ^ (row_in_tile & 7)) << 4)) = v;
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-      }
-      mbar_arrive(&p_full[t]);
-    }
-
-    // epilogue: O / l
-    mbar_wait(&o_done[t], (n_tiles - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l;
-    const bool valid_row = q_row < p.nq;
-    const int b = bh / p.heads, h = bh - b * p.heads;
-    bf16* orow = p.out + ((int64_t)b * p.nq + q_row) * (p.heads * 64) + h * 64;
-#pragma unroll
-    for (int c = 0; c < 64; c += 32) {
-      uint32_t o[32];
-      LD_TMEM_LD32(to + c, o);
-      tmem_ld_wait();
-      if (valid_row) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[g * 8 + i]) * inv_l;
-          uint4 v;
-          v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
-          v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
-          *reinterpret_cast<uint4*>(orow + c + g * 8) = v;
-          if (p.out_f32 != nullptr) {
-            float* of = p.out_f32 + ((int64_t)bh * p.nq + q_row) * 64 + c + g * 8;
-            *reinterpret_cast<float4*>(of) = make_float4(f[0], f[1], f[2], f[3]);
-            *reinterpret_cast<float4*>(of + 4) = make_float4(f[4], f[5], f[6], f[7]);
-          }
-        }
-      }
-    }
-    if (valid_row && p.lse != nullptr) p.lse[(int64_t)bh * p.nq + q_row] = m_used * sl2 + log2f(l);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
-}
-
-
-// ------------------------------------------------------------------------------------------------------------
-// Second-generation kernel: 64-key sub-blocks with the score buffer of every query tile DOUBLE-BUFFERED in TMEM.
-//
-// In attn_kernel the chain  softmax(t,j) -> PV(t,j) -> S(t,j+1) -> softmax(t,j+1)  is serial per query tile (P
-// aliases S, so the next S cannot start before the PV that reads P), and the two tiles' exponential phases
-// collide on the 16-op/clk MUFU unit: ~3300 clk per 128 keys against a 2048-clk MUFU floor.  Here S(t,i+2) is
-// issued right after PV(t,i) into the buffer PV(t,i) just released, so S(t,i+1) is always complete when the
-// softmax of sub-block i finishes; the softmax warps never wait for the tensor pipe and the kernel runs at the
-// MUFU (or, with the polynomial split, the issue-slot) bound.
-//   TMEM columns: S/P(t,b) at (2t+b)*64 [0,256) ; O_t at 256+64t [256,384).
-//   K/V still travel as 128-row TMA boxes (two sub-blocks per box).
-constexpr int kKS2 = 4;
-constexpr int kAttn2Smem = 2 * kTileBytes + 2 * kKS2 * kTileBytes + 1024 + 256;
-
-template <int POLY_EVERY, bool PROF>
-__global__ void __launch_bounds__(kAttnThreads, 1)
-attn2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-             const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                // 2 tiles
-  uint8_t* sK = sQ + 2 * kTileBytes;                 // kKS2 tiles
-  uint8_t* sV = sK + kKS2 * kTileBytes;              // kKS2 tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKS2 * kTileBytes);
-  uint64_t* q_full = bars;               // 1
-  uint64_t* k_full = bars + 1;           // kKS2
-  uint64_t* k_empty = k_full + kKS2;
-  uint64_t* v_full = k_empty + kKS2;
-  uint64_t* v_empty = v_full + kKS2;
-  uint64_t* s_full = v_empty + kKS2;     // [t][b] = 4
-  uint64_t* p_full = s_full + 4;         // [t][b] = 4
-  uint64_t* o_done = p_full + 4;         // 2
-  uint64_t* all_done = o_done + 2;       // 1: every MMA of this CTA has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q_blocks = (p.nq + 255) / 256;
-  const int bh = blockIdx.x / q_blocks;
-  const int q0 = (blockIdx.x % q_blocks) * 256;
-  const int n_tiles = (p.nkv + 127) / 128;   // TMA boxes
-  const int n_sub = (p.nkv + 63) / 64;       // 64-key sub-blocks
-  // PROF: event trace of one CTA (first 64 sub-blocks): trace[role][i][event], role 0 = MMA issuer, 1/2 = first
-  // softmax warp of tile 0/1
-  long long* trace = nullptr;
-  if constexpr (PROF) {
-    if (p.prof != nullptr && blockIdx.x == p.trace_cta) trace = p.prof + (int64_t)gridDim.x * 96;
-  }
-#define LD_TRACE(role, i, ev)                                                   \
-  if constexpr (PROF) {                                                         \
-    if (trace != nullptr && (i) < 64) trace[((role) * 64 + (i)) * 8 + (ev)] = clock64(); \
-  }
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < kKS2; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
-    }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
-    }
-    mbar_init(&o_done[0], 1);
-    mbar_init(&o_done[1], 1);
-    mbar_init(all_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // Warps 0 and 1 run warp-uniform code and issue through an elect.sync leader: ptxas then emits back-to-back
-  // UTMALDG / UTCHMMA instead of a per-instruction divergence loop (measured: ~100 clk -> 32 clk per MMA).
-  if (warp < 4) {
-    reg_dealloc<56>();
-    if (warp == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      const bool leader = elect_one();
-      if (leader) {
-        mbar_expect_tx(q_full, 2 * kTileBytes);
-        tma_load_3d(sQ, &tmap_q, q_full, 0, q0, bh);
-        tma_load_3d(sQ + kTileBytes, &tmap_q, q_full, 0, q0 + 128, bh);
-      }
-      int s = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(&k_empty[s], ph ^ 1);
-        if (leader) {
-          mbar_expect_tx(&k_full[s], kTileBytes);
-          tma_load_3d(sK + s * kTileBytes, &tmap_k, &k_full[s], 0, j * 128, bh);
-        }
-        mbar_wait(&v_empty[s], ph ^ 1);
-        if (leader) {
-          mbar_expect_tx(&v_full[s], kTileBytes);
-          tma_load_3d(sV + s * kTileBytes, &tmap_v, &v_full[s], 0, j * 128, bh);
-        }
-        if (++s == kKS2) { s = 0; ph ^= 1; }
-      }
-    } else if (warp == 1) {
-      // ---------------------------------------------------------------- MMA issuer
-      const bool leader = elect_one();
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);  // B (=V) is N-major
-      const uint64_t qdesc = make_sdesc_sw128(smem_u32(sQ));
-      const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK));
-      const uint64_t vdesc = make_sdesc_sw128(smem_u32(sV));
-      // descriptor address units are 16 B: ring stage = 1024, 64-row half = 512, query tile = 1024
-      // S(t, i) = Q_t K_i^T into buffer i&1; K sub-block i = rows [64*(i&1), +64) of ring stage (i>>1)%kKS2
-      auto issue_s = [&](int t, int i) {
-        const uint64_t adesc = qdesc + uint32_t(t * (kTileBytes >> 4));
-        const uint64_t bdesc = kdesc + uint32_t(((i >> 1) % kKS2) * (kTileBytes >> 4) + (i & 1) * (kTileBytes >> 5));
-        const uint32_t d = tmem_base + (2 * t + (i & 1)) * 64;
-        if (leader) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(&s_full[2 * t + (i & 1)]);
-        }
-      };
-      // O_t += P(t,i) V_i ; P: 128 lanes x 64 keys bf16 = 32 TMEM columns over S(t, i&1)
-      auto issue_pv = [&](int t, int i) {
-        const uint64_t bdesc = vdesc + uint32_t(((i >> 1) % kKS2) * (kTileBytes >> 4) + (i & 1) * (kTileBytes >> 5));
-        const uint32_t d = tmem_base + 256 + t * 64;
-        const uint32_t a = tmem_base + (2 * t + (i & 1)) * 64;
-        if (leader) {
-          // 16 keys per step: 16 rows x 128 B = 2048 B (encoded 128)
-          umma_ts(d, a, bdesc, idesc_o, i != 0);
-#pragma unroll
-          for (int k = 1; k < 4; ++k) umma_ts(d, a + k * 8, bdesc + 128 * k, idesc_o, 1u);
-          umma_commit(&o_done[t]);
-        }
-      };
-      auto k_wait = [&](int tile) { mbar_wait(&k_full[tile % kKS2], (tile / kKS2) & 1); };
-      auto v_wait = [&](int tile) { mbar_wait(&v_full[tile % kKS2], (tile / kKS2) & 1); };
-
-      mbar_wait(q_full, 0);
-      k_wait(0);
-      tc_fence_after();
-      issue_s(0, 0);
-      issue_s(1, 0);
-      if (n_sub > 1) {
-        issue_s(0, 1);
-        issue_s(1, 1);
-      }
-      if (leader) umma_commit(&k_empty[0]);
-      long long w_kv = 0, w_p0 = 0, w_p1 = 0, t_all = 0, w_ipv = 0, w_is = 0;
-      if constexpr (PROF) t_all = clock64();
-      for (int i = 0; i < n_sub; ++i) {
-        const int b = i & 1;
-        const uint32_t par = (i >> 1) & 1;
-        const bool has_next = (i + 2) < n_sub;
-        long long c0 = 0;
-        if constexpr (PROF) c0 = clock64();
-        if (b == 0) v_wait(i >> 1);
-        if (has_next && b == 0) k_wait((i + 2) >> 1);
-        if constexpr (PROF) { const long long c1 = clock64(); w_kv += c1 - c0; c0 = c1; }
-        // tile 0
-        mbar_wait(&p_full[0 + b], par);
-        if constexpr (PROF) { const long long c1 = clock64(); w_p0 += c1 - c0; c0 = c1; }
-        if (leader) { LD_TRACE(0, i, 0); }
-        tc_fence_after();
-        issue_pv(0, i);
-        if constexpr (PROF) { const long long c1 = clock64(); w_ipv += c1 - c0; c0 = c1; }
-        if (has_next) issue_s(0, i + 2);
-        if constexpr (PROF) { const long long c1 = clock64(); w_is += c1 - c0; c0 = c1; }
-        if (leader) { LD_TRACE(0, i, 1); }
-        // tile 1
-        if constexpr (PROF) c0 = clock64();
-        mbar_wait(&p_full[2 + b], par);
-        if constexpr (PROF) w_p1 += clock64() - c0;
-        if (leader) { LD_TRACE(0, i, 2); }
-        tc_fence_after();
-        issue_pv(1, i);
-        if (leader && (b == 1 || i == n_sub - 1)) umma_commit(&v_empty[(i >> 1) % kKS2]);
-        if (has_next) {
-          issue_s(1, i + 2);
-          if (leader && (b == 1 || i + 2 == n_sub - 1)) umma_commit(&k_empty[((i + 2) >> 1) % kKS2]);
-        }
-        if (leader) { LD_TRACE(0, i, 3); }
-      }
-      if (leader) umma_commit(all_done);
-      if constexpr (PROF) {
-        if (leader && p.prof != nullptr) {
-          long long* d = p.prof + ((int64_t)blockIdx.x * 12 + 1) * 8;
-          d[0] = w_kv; d[1] = w_p0; d[2] = w_p1; d[3] = clock64() - t_all; d[4] = w_ipv; d[5] = w_is;
-        }
-      }
-    }
-  } else {
-    reg_alloc<208>();
-    // ------------------------------------------------------------------ softmax / correction / epilogue
-    const int t = (warp - 4) >> 2;        // query tile 0/1
-    const int quad = warp & 3;
-    const int row_in_tile = quad * 32 + lane;
-    const int q_row = q0 + t * 128 + row_in_tile;
-    const uint32_t lane_base = uint32_t(quad * 32) << 16;
-    const uint32_t ts = tmem_base + lane_base + t * 128;       // S(t,0); S(t,1) is 64 columns further
-    const uint32_t to = tmem_base + lane_base + 256 + t * 64;  // O_t
-    const float sl2 = p.scale_log2;
-
-    float m_used = -INFINITY;  // raw-score units
-    float l = 0.f;
-    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
-    long long tp = 0;
+// PROF kernels accumulate per-phase cycle counters (tools/attn_phase_prof.py).
 #define LD_PROF(slot)                                  \
   if constexpr (PROF) {                                \
     const long long now = clock64();                   \
     prof_acc[slot] += now - tp;                        \
     tp = now;                                          \
   }
-    if (t == 1 && p.stagger > 0) {
-      // The two query tiles share each SMSP's MUFU unit.  Their phase offset is preserved by the dynamics (the
-      // tile that enters its exponential phase later is slowed by exactly the overlap), so start tile 1 half a
-      // period late: one tile's exponentials then overlap the other's load / max / store phases for the whole run.
-      mbar_wait(&s_full[2], 0);
-      const long long t_start = clock64();
-      while (clock64() - t_start < p.stagger) {
-      }
-    }
-    if constexpr (PROF) tp = clock64();
-    for (int i = 0; i < n_sub; ++i) {
-      const int b = i & 1;
-      const uint32_t tsb = ts + b * 64;
-      mbar_wait(&s_full[2 * t + b], (i >> 1) & 1);
-      tc_fence_after();
-      LD_PROF(0);
-      if (quad == 0 && lane == 0) { LD_TRACE(1 + t, i, 0); }
-      uint32_t s[64];
-      LD_TMEM_LD32(tsb + 0, (s + 0));
-      LD_TMEM_LD32(tsb + 32, (s + 32));
-      tmem_ld_wait();
-      LD_PROF(1);
-      if (quad == 0 && lane == 0) { LD_TRACE(1 + t, i, 1); }
-      const int valid = p.nkv - i * 64;
-      if (valid < 64) {
-#pragma unroll
-        for (int c = 0; c < 64; ++c)
-          if (c >= valid) s[c] = 0xff800000u;  // -inf
-      }
-      float mx4[4] = {__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]), __uint_as_float(s[3])};
-#pragma unroll
-      for (int c = 4; c < 64; c += 4) {
-        mx4[0] = fmaxf(mx4[0], __uint_as_float(s[c]));
-        mx4[1] = fmaxf(mx4[1], __uint_as_float(s[c + 1]));
-        mx4[2] = fmaxf(mx4[2], __uint_as_float(s[c + 2]));
-        mx4[3] = fmaxf(mx4[3], __uint_as_float(s[c + 3]));
-      }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-
-      bool need = (i > 0) && ((mx - m_used) * sl2 > kRescaleThreshold);
-      if (i == 0) m_used = mx;
-      if (__any_sync(0xffffffffu, need)) {
-        // lazy correction: bring O_t and l to the new reference maximum (whole warp, tcgen05.ld/st are collective)
-        const float m_new = fmaxf(m_used, mx);
-        const float alpha = ex2((m_used - m_new) * sl2);
-        mbar_wait(&o_done[t], (i - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 64; c += 32) {
-          uint32_t o[32];
-          LD_TMEM_LD32(to + c, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-          LD_TMEM_ST32(to + c, o);
-        }
-        l *= alpha;
-        m_used = m_new;
-      }
-      const float msc = m_used * sl2;
-      LD_PROF(2);
-      if (quad == 0 && lane == 0) { LD_TRACE(1 + t, i, 2); }
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-      uint32_t pk[32];
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        float pv[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int idx = 4 * c + e;
-          const float x = fmaf(__uint_as_float(s[idx]), sl2, -msc);
-          if constexpr (POLY_EVERY > 0) {
-            pv[e] = ((idx % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x) : ex2(x);
-          } else {
-            pv[e] = ex2(x);
-          }
-        }
-        sum0 += pv[0];
-        sum1 += pv[1];
-        sum2 += pv[2];
-        sum3 += pv[3];
-        pk[2 * c] = pack_bf16x2(pv[0], pv[1]);
-        pk[2 * c + 1] = pack_bf16x2(pv[2], pv[3]);
-      }
-      l += (sum0 + sum1) + (sum2 + sum3);
-      LD_PROF(3);
-      if (quad == 0 && lane == 0) { LD_TRACE(1 + t, i, 3); }
-      LD_TMEM_ST32(tsb, pk);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_full[2 * t + b]);
-      LD_PROF(4);
-      if (quad == 0 && lane == 0) { LD_TRACE(1 + t, i, 4); }
-    }
-
-    // epilogue: O / l
-    // the softmax may run up to two PVs ahead of the tensor pipe, so a parity wait on o_done could alias here:
-    // the end of all MMAs has its own single-use barrier
-    mbar_wait(all_done, 0);
-    tc_fence_after();
-    if constexpr (PROF) {
-      if (lane == 0 && p.prof != nullptr) {
-        long long* d = p.prof + ((int64_t)blockIdx.x * 12 + warp) * 8;
-        for (int e = 0; e < 6; ++e) d[e] = prof_acc[e];
-      }
-    }
-    const float inv_l = 1.0f / l;
-    const bool valid_row = q_row < p.nq;
-    const int bb = bh / p.heads, h = bh - bb * p.heads;
-    bf16* orow = p.out + ((int64_t)bb * p.nq + q_row) * (p.heads * 64) + h * 64;
-#pragma unroll
-    for (int c = 0; c < 64; c += 32) {
-      uint32_t o[32];
-      LD_TMEM_LD32(to + c, o);
-      tmem_ld_wait();
-      if (valid_row) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(o[g * 8 + e]) * inv_l;
-          uint4 v;
-          v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
-          v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
-          *reinterpret_cast<uint4*>(orow + c + g * 8) = v;
-          if (p.out_f32 != nullptr) {
-            float* of = p.out_f32 + ((int64_t)bh * p.nq + q_row) * 64 + c + g * 8;
-            *reinterpret_cast<float4*>(of) = make_float4(f[0], f[1], f[2], f[3]);
-            *reinterpret_cast<float4*>(of + 4) = make_float4(f[4], f[5], f[6], f[7]);
-          }
-        }
-      }
-    }
-    if (valid_row && p.lse != nullptr) p.lse[(int64_t)bh * p.nq + q_row] = m_used * sl2 + log2f(l);
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
-}
-
 
 // ------------------------------------------------------------------------------------------------------------
 // Third-generation kernel: FOUR independent online-softmax streams per CTA, 16 softmax warps (4 per SMSP).
@@ -1442,34 +790,6 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(float* __restrict__ o_a
   if ((gid & 15) == 0) lse_acc[row] = m + log2f(wa + wb);
 }
 
-template <bool P_IN_TMEM, int POLY_EVERY>
-static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& prm,
-                       int grid, cudaStream_t st) {
-  auto kern = attn_kernel<P_IN_TMEM, POLY_EVERY>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    attr_set = true;
-  }
-  kern<<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, prm);
-  LD_CHECK_CUDA(cudaGetLastError());
-  return LD_OK;
-}
-
-template <int POLY_EVERY, bool PROF = false>
-static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& prm,
-                        int grid, cudaStream_t st) {
-  auto kern = attn2_kernel<POLY_EVERY, PROF>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2Smem));
-    attr_set = true;
-  }
-  kern<<<grid, kAttnThreads, kAttn2Smem, st>>>(tq, tk, tv, prm);
-  LD_CHECK_CUDA(cudaGetLastError());
-  return LD_OK;
-}
-
 template <int POLY_EVERY, bool PROF = false>
 static int launch_attn3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& prm,
                         int grid, cudaStream_t st) {
@@ -1557,66 +877,34 @@ extern "C" int ld_attention_bf16(const void* q, const void* k, const void* v, vo
   prm.nq = nq;
   prm.nkv = nkv;
   prm.prof = nullptr;
-  prm.trace_cta = 0;
   prm.redo = nullptr;
   prm.redo_only = 0;
   prm.q = (const bf16*)q;
   prm.q_rows = q_rows;
-  {
-    static int stagger = -1;
-    if (stagger < 0) {
-      const char* e = getenv("LD_ATTN_STAGGER");
-      stagger = e ? atoi(e) : 540;
-    }
-    prm.stagger = stagger;
-  }
   prm.scale_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   const int grid = BH * ((nq + 255) / 256);
-  // variant: bit 0 = P through shared memory instead of TMEM; bits 1.. = exponential split
-  //   0: default (P in TMEM, every 4th exp on the FMA pipe)   1: P via smem, all MUFU
-  //   2: P in TMEM, all MUFU   4: every 3rd exp polynomial   6: every 2nd   8: every 4th (same as 0)
+  // variant 0: attn4_kernel (fixed first-block reference maximum) + exact fix-up launch   1: exact kernel only
+  //         (attn3_kernel: per-block maxima, lazy rescaling)   2 / 3: attn4 with every 4th / 3rd exponential on the
+  //         FMA pipe (polynomial)
   cudaStream_t st = (cudaStream_t)stream;
   switch (variant) {
-    case 0:
-    case 8: return launch_attn<true, 4>(tq, tk, tv, prm, grid, st);
-    case 1: return launch_attn<false, 0>(tq, tk, tv, prm, grid, st);
-    case 2: return launch_attn<true, 0>(tq, tk, tv, prm, grid, st);
-    case 4: return launch_attn<true, 3>(tq, tk, tv, prm, grid, st);
-    case 6: return launch_attn<true, 2>(tq, tk, tv, prm, grid, st);
-    // second-generation kernel (double-buffered 64-key score blocks): 16 all MUFU, 17/18/19 every 4th/3rd/2nd polynomial
-    case 16:
-      if (g_attn_prof != nullptr) {
-        prm.prof = g_attn_prof;
-        { const char* e = getenv("LD_ATTN_TRACE_CTA"); prm.trace_cta = e ? atoi(e) : 0; }
-        return launch_attn2<0, true>(tq, tk, tv, prm, grid, st);
-      }
-      return launch_attn2<0>(tq, tk, tv, prm, grid, st);
-    case 17: return launch_attn2<4>(tq, tk, tv, prm, grid, st);
-    case 18: return launch_attn2<3>(tq, tk, tv, prm, grid, st);
-    case 19: return launch_attn2<2>(tq, tk, tv, prm, grid, st);
-    // third-generation kernel (four softmax streams): 32 all MUFU, 33/34/35 every 4th/3rd/2nd polynomial
-    case 32:
+    case 1:
       if (g_attn_prof != nullptr) {
         prm.prof = g_attn_prof;
         return launch_attn3<0, true>(tq, tk, tv, prm, grid, st);
       }
       return launch_attn3<0>(tq, tk, tv, prm, grid, st);
-    case 33: return launch_attn3<4>(tq, tk, tv, prm, grid, st);
-    case 34: return launch_attn3<3>(tq, tk, tv, prm, grid, st);
-    case 35: return launch_attn3<2>(tq, tk, tv, prm, grid, st);
-    // fourth-generation kernel (double-buffered scores + column-split warp pairs + Q in TMEM): 48 all MUFU,
-    // 49/50 every 4th/3rd polynomial
-    case 48:
-    case 49:
-    case 50: {
+    case 0:
+    case 2:
+    case 3: {
       rc = redo_buffer(grid, &prm.redo);
       if (rc != LD_OK) return rc;
-      if (variant == 48 && g_attn_prof != nullptr) {
+      if (variant == 0 && g_attn_prof != nullptr) {
         prm.prof = g_attn_prof;
         rc = launch_attn4<0, true>(tk, tv, prm, grid, st);
-      } else if (variant == 48) {
+      } else if (variant == 0) {
         rc = launch_attn4<0>(tk, tv, prm, grid, st);
-      } else if (variant == 49) {
+      } else if (variant == 2) {
         rc = launch_attn4<4>(tk, tv, prm, grid, st);
       } else {
         rc = launch_attn4<3>(tk, tv, prm, grid, st);

@@ -81,8 +81,12 @@ typedef struct ld_gemm_args {
 int ld_gemm_bf16(const ld_gemm_args* args, void* stream);
 
 /* ---- full (non-causal) self-attention, head_dim 64, flash-style online softmax on tcgen05 ------------- */
-/* q: [BH, q_rows, 64], k/v: [BH, kv_rows, 64] bf16 (q pre-multiplied by scale*log2e, see LD_EPI_QKV).
+/* q: [BH, q_rows, 64], k/v: [BH, kv_rows, 64] bf16; scores are scaled by 1/sqrt(64) inside the kernel.
    Uses q rows [0,nq) and kv rows [0,nkv).  out: bf16 [B, nq, heads*64] (token-major, ready for `dense`).
+   variant: 0 = default (fixed per-row reference maximum + exact fix-up launch for overflowed CTAs), 1 = exact kernel
+   only (per-block maxima, lazy rescaling), 2 / 3 = default with every 4th / 3rd exponential as an FMA-pipe polynomial.
+   Keeps one process-wide scratch array of per-CTA redo flags (allocated on first use), so concurrent calls must be
+   on the same stream.
    If lse != NULL also writes fp32 log2-sum-exp [BH, nq] and, when out_f32 != NULL, the normalised fp32 output
    [BH, nq, 64] (used by the ring merge).  Replaces SAT attention_fn_default -> F.scaled_dot_product_attention
    reached through dit_video_concat.py:655-664. */

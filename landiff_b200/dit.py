@@ -243,7 +243,7 @@ class DiffusionTransformer(nn.Module):
         self.compressed_num_frames = (num_frames - 1) // time_compressed_rate + 1
         self._build_modules(modules)
         self._ws = {}
-        self.attn_variant = 48
+        self.attn_variant = 0
         self.shard: Optional[SequenceShard] = None   # explicit token shard (tests); normally derived from sp_layout
         self.sp_layout = None                        # set by landiff_b200.parallel.attach for ring SP
         self.ring = None                             # set by landiff_b200.parallel.attach

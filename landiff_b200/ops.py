@@ -125,7 +125,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epilogue: int, bias: Optional[torc
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, nq: Optional[int] = None, nkv: Optional[int] = None,
               out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
-              out_f32: Optional[torch.Tensor] = None, variant: int = 48) -> torch.Tensor:
+              out_f32: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
     """softmax(q k^T / 8) v for q,k,v [B, H, rows, 64] bf16 -> [B, nq, H*64] bf16 (full attention)."""
     for n_, t_ in (("q", q), ("k", k), ("v", v)):
         _chk(t_, BF16, n_)

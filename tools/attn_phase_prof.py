@@ -1,4 +1,4 @@
-"""Per-phase cycle breakdown of the attention kernel's softmax warps and MMA issuer (debug variant of attn2_kernel).
+"""Per-phase cycle breakdown of the attention kernels' softmax warps and MMA issuers (PROF template variants).
 usage: python tools/attn_phase_prof.py [N]"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,10 +13,10 @@ k = torch.randn(B, H, N, 64, device=dev).bfloat16()
 v = torch.randn(B, H, N, 64, device=dev).bfloat16()
 out = torch.empty(B, N, H * 64, device=dev, dtype=torch.bfloat16)
 grid = B * H * ((N + 255) // 256)
-VAR = int(os.environ.get("LD_ATTN_VARIANT", "32"))
-NW = 20 if VAR >= 32 else 12
-FIRST, LAST, MMAW = (0, 16, 19) if VAR >= 48 else (4, NW, 1)
-prof_all = torch.zeros(grid * NW * 8 + 3 * 64 * 8, device=dev, dtype=torch.int64)
+VAR = int(os.environ.get("LD_ATTN_VARIANT", "0"))   # 0: attn4_kernel, 1: attn3_kernel
+NW = 20
+FIRST, LAST, MMAW = (0, 16, 19) if VAR == 0 else (4, NW, 1)
+prof_all = torch.zeros(grid * NW * 8, device=dev, dtype=torch.int64)
 prof = prof_all[:grid * NW * 8].view(grid, NW, 8)
 lib = _C.load()
 lib.ld_debug_attn_prof.argtypes = [ctypes.c_void_p]
@@ -28,7 +28,7 @@ ops.attention(q, k, v, out=out, variant=VAR)
 torch.cuda.synchronize()
 lib.ld_debug_attn_prof(None)
 n_sub = (N + 63) // 64
-per_warp = n_sub if (VAR < 32 or VAR >= 48) else n_sub / 2
+per_warp = n_sub if VAR == 0 else n_sub / 2
 p = prof.double().cpu()
 sm = p[:, FIRST:LAST, :5].mean(dim=(0, 1)) / per_warp
 names = ["wait s_full", "tcgen05.ld", "mask+max+rescale", "exp+sum+pack", "st+fence+arrive"]
@@ -36,6 +36,6 @@ print(f"variant {VAR} N={N} n_sub={n_sub}: softmax warp cycles per 64-key sub-bl
 for n, c in zip(names, sm.tolist()):
     print(f"  {n:20s} {c:8.1f}")
 print(f"  {'total':20s} {sm.sum().item():8.1f}")
-for w in ((18, 19) if VAR >= 48 else (MMAW,)):
+for w in ((18, 19) if VAR == 0 else (MMAW,)):
     mm = p[:, w, :6].mean(dim=0) / n_sub
     print("MMA issuer warp %d per sub-block: wait k/v %.1f  wait p_full %.1f  (%.1f)  loop total %.1f  issue PV %.1f  issue S %.1f" % ((w,) + tuple(mm.tolist())))
