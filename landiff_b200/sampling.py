@@ -189,11 +189,14 @@ class VPSDEDPMPP2MSampler:
     @torch.no_grad()
     def sample(self, network: Callable, x: torch.Tensor, cond: Dict, uc: Dict, num_steps: Optional[int] = None,
                cfg_group=None, step_callback=None, start_step: int = 0, max_steps: Optional[int] = None,
-               **kwargs) -> torch.Tensor:
+               noise_fn: Optional[Callable] = None, **kwargs) -> torch.Tensor:
         """Fast path: drives `network(x2, t2, cond2, idx=t2)` (batch = [uncond, cond]) directly and applies
         `ld_sampler_update` once per step.  With `cfg_group` (a landiff_b200.parallel.CFGGroup) each rank evaluates
         one batch row and the two bf16 outputs are exchanged over NCCL.  `start_step` / `max_steps` run a slice of
-        the schedule (benchmarking); a slice that does not start at 0 begins without DPM++ history."""
+        the schedule (benchmarking); a slice that does not start at 0 begins without DPM++ history.  `noise_fn(x)`
+        replaces `torch.randn_like` (same draw order as the reference: one draw per step, a second one on every step
+        after the first) so a trajectory can be replayed against a CPU noise stream."""
+        randn = torch.randn_like if noise_fn is None else noise_fn
         acs, timesteps = self.prepare_sampling_loop(num_steps)
         n = len(acs) - 1
         total = self.num_steps if num_steps is None else num_steps
@@ -229,12 +232,12 @@ class VPSDEDPMPP2MSampler:
                                    den_out=den_out)
             else:
                 m1, m2, m3, m4, mn = self.step_scalars(a_prev, a, a_next)
-                eps = torch.randn_like(x)  # x_standard's draw (sampling.py:771)
+                eps = randn(x)  # x_standard's draw (sampling.py:771)
                 if old is None or float(a_next) < 1e-14:
                     ops.sampler_update(x, net_u, net_c, None, eps, c_skip=c_skip, c_out=c_out, cfg=cfg, m1=m1, m2=m2, mn=mn,
                                        mode=0, x_out=x_next, den_out=den_out)
                 else:
-                    eps = torch.randn_like(x)  # the reference draws a second tensor for x_advanced (:776-781)
+                    eps = randn(x)  # the reference draws a second tensor for x_advanced (:776-781)
                     ops.sampler_update(x, net_u, net_c, old, eps, c_skip=c_skip, c_out=c_out, cfg=cfg, m1=m1, m2=m2, m3=m3,
                                        m4=m4, mn=mn, mode=1, x_out=x_next, den_out=den_out)
             old = den_out

@@ -107,3 +107,43 @@ def test_config1_against_cpu_oracle(strong):
     ref = O.warp_forward(O.cast_state_dict(sdc, torch.float32), O.cast_state_dict(sdm, torch.float32), cfg_o, x, t, ctx, sem)
     r, c = rel(out, ref), cos(out, ref)
     assert r <= REL_TOL and c >= COS_TOL, f"rel-L2 {r:.3e} cos {c:.6f}"
+
+
+def test_50_step_trajectory_psnr():
+    """BASELINE.json north_star: the 50-step end-to-end latent must match the reference GPU-free fp32 path within
+    PSNR >= 35 dB.  Golden = the CPU oracle's 50-step DPM++(2M) SDE CFG trajectory at config 1 (full depth) on the
+    seeded weights, generated by oracle/make_trajectory_golden.py; here the same noise stream is replayed through
+    the CUDA path (drop-in network + fused sampler update)."""
+    from landiff_b200.sampling import VPSDEDPMPP2MSampler
+    from oracle.make_trajectory_golden import SEED_NOISE, inputs
+
+    gold = torch.load(GOLDEN / "trajectory50_config1.pt", weights_only=False)
+    cfg_o = O.CONFIG1
+    sdc = O.random_state_dict(cfg_o, True, seed=10)
+    sdm = O.random_state_dict(cfg_o, False, seed=11)
+    x, ctx, sem = inputs(cfg_o)
+    warp = build_warp(CONFIG1, device="cuda", sd_ctrl=sdc, sd_main=sdm)
+    dit.InferValueRegistry.clear()
+    dit.InferValueRegistry.register("semantic_feature", sem.cuda())
+    gen = torch.Generator().manual_seed(SEED_NOISE)
+    noise = lambda t: torch.randn(t.shape, generator=gen).to(t.device)
+    sampler = VPSDEDPMPP2MSampler(num_steps=50, device="cuda")
+    trace = {}
+    cond = {"crossattn": ctx.cuda().bfloat16()}
+    uc = {"crossattn": torch.zeros_like(cond["crossattn"])}
+    out = sampler.sample(warp, x.cuda(), cond, uc, noise_fn=noise,
+                         step_callback=lambda i, xs: trace.__setitem__(i, xs.float().cpu().clone()))
+    torch.cuda.synchronize()
+    dit.InferValueRegistry.clear()
+
+    def psnr(a, b):
+        mse = ((a.double() - b.double()) ** 2).mean()
+        peak = b.double().abs().max()
+        return float(10 * torch.log10(peak ** 2 / mse))
+
+    for i, ref in gold["steps"].items():
+        p = psnr(trace[i], ref)
+        assert p >= 35.0, f"step {i + 1}: PSNR {p:.1f} dB"
+    p = psnr(out.float().cpu(), gold["final"])
+    print(f"50-step final latent PSNR {p:.1f} dB, rel-L2 {rel(out.float().cpu(), gold['final']):.3e}")
+    assert p >= 35.0, f"final latent PSNR {p:.1f} dB < 35"
