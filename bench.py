@@ -218,6 +218,11 @@ def run_ours(args):
         nq = cfg.n_tok // layout.sp_size
         flop_per_launch = 4.0 * nq * nq * 64 * b_rows * cfg.num_heads
         attn_avg = sum(attn_ms) / max(len(attn_ms), 1)
+        # DRAM traffic of one attention launch from the `ncu --set full` capture of the same kernel and shape at B = 1
+        # (profiles/r1_ncu_attn4.csv: dram__bytes_read.sum 205.7 MB + dram__bytes_write.sum 51.6 MB); the launch is
+        # independent per batch row, so B rows move B times that.  Algorithmic bytes (Q, K, V in, O out) = 273 MB per
+        # row: K/V re-reads of the 70 query blocks of a head are served by L2 (hit rate 94.7 %).  Ring shards: no capture.
+        traffic = 257.2e6 * b_rows if layout.sp_size == 1 else None
         achieved = flop_per_launch / (attn_avg * 1e-3) / 1e12 if attn_avg > 0 else 0.0
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -232,7 +237,9 @@ def run_ours(args):
             "tensor_frac_of_peak_whole_step": round(FLOP_PER_CFG_STEP_FULL / (ms_per_step * 1e-3) / world / 1e12 / tf_peak, 4),
             "roofline": {"bound": "tensor", "kernel": "attn4_kernel (tcgen05 flash attention, head_dim 64: double-buffered scores, 16 softmax warps, Q in TMEM)",
                          "achieved": round(achieved, 1), "peak": tf_peak, "unit": "TFLOP/s",
-                         "frac": round(achieved / tf_peak, 4), "traffic": None, "peak_source": how,
+                         "frac": round(achieved / tf_peak, 4), "traffic": traffic,
+                         "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r1_ncu_attn4.csv)",
+                         "peak_source": how,
                          "launch_ms": round(attn_avg, 4), "launches_timed": len(attn_ms),
                          "share_of_step": round(sum(attn_ms) / ms, 4) if ms > 0 else None},
             "e2e": {"value": round(e2e_ms * SAMPLER_STEPS / 1e3, 4), "unit": UNIT,

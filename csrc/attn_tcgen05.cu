@@ -822,19 +822,23 @@ static int launch_attn4(const CUtensorMap& tk, const CUtensorMap& tv, const Attn
 
 using namespace ld;
 
-// redo flags of the attn4 + fix-up pair: one int per CTA, grown on demand (allocation only on first use / growth)
-static int* g_redo = nullptr;
-static int g_redo_cap = 0;
+// redo flags of the attn4 + fix-up pair: one int per CTA, per device, grown on demand (allocation only on first use
+// or growth, so a warmed-up step allocates nothing)
+static int* g_redo[64] = {nullptr};
+static int g_redo_cap[64] = {0};
 static int redo_buffer(int grid, int** out) {
-  if (grid > g_redo_cap) {
-    if (g_redo != nullptr) LD_CHECK_CUDA(cudaFree(g_redo));
-    g_redo = nullptr;
-    g_redo_cap = 0;
+  int dev = 0;
+  LD_CHECK_CUDA(cudaGetDevice(&dev));
+  LD_CHECK_ARG(dev >= 0 && dev < 64, "ld_attention_bf16: device index out of range");
+  if (grid > g_redo_cap[dev]) {
+    if (g_redo[dev] != nullptr) LD_CHECK_CUDA(cudaFree(g_redo[dev]));
+    g_redo[dev] = nullptr;
+    g_redo_cap[dev] = 0;
     const int cap = grid + grid / 2 + 1024;
-    LD_CHECK_CUDA(cudaMalloc(&g_redo, sizeof(int) * (size_t)cap));
-    g_redo_cap = cap;
+    LD_CHECK_CUDA(cudaMalloc(&g_redo[dev], sizeof(int) * (size_t)cap));
+    g_redo_cap[dev] = cap;
   }
-  *out = g_redo;
+  *out = g_redo[dev];
   return LD_OK;
 }
 
