@@ -415,7 +415,7 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 
 
 // ------------------------------------------------------------------------------------------------------------
-// Fourth-generation kernel: double-buffered 64-key score blocks (attn2) + 16 softmax warps (attn3) + Q in TMEM,
+// Fourth-generation kernel: double-buffered 64-key score blocks + 16 softmax warps + Q in TMEM,
 // and NO per-block row maximum.
 //
 // Two 128-row query tiles per CTA; each tile has two 64-column score buffers in TMEM so S(t,i+2) is issued right

@@ -98,6 +98,20 @@ int ld_attention_bf16(const void* q, const void* k, const void* v, void* out, fl
 int ld_attention_merge(float* o_acc, float* lse_acc, const float* o_new, const float* lse_new, void* out_bf16,
                        int batch, int heads, int nq, void* stream);
 
+/* ---- copy-engine ring transport (sequence-parallel attention, csrc/peer_ring.cu) ------------------------- */
+/* K|V shards rotate between the GPUs of one NVLink domain as cudaMemcpyAsync peer copies (no SMs) into buffers the
+   receiver exports with CUDA IPC; cross-process ordering by 32-bit stream memory operations.  Replaces the NCCL
+   send/recv hop of landiff_b200/parallel.py; the reference has no sequence parallelism.
+   ld_ipc_alloc: cudaMalloc + zero + export (64-byte cudaIpcMemHandle_t).  ld_ipc_open maps a peer's export into this
+   process (lazy peer access).  ld_stream_wait_geq_u32 waits until (int32)(*addr - value) >= 0. */
+int ld_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char handle_out[64]);
+int ld_ipc_open(const unsigned char handle[64], void** dev_ptr);
+int ld_ipc_close(void* dev_ptr);
+int ld_ipc_free(void* dev_ptr);
+int ld_copy_async(void* dst, const void* src, size_t bytes, void* stream);
+int ld_stream_write_u32(void* dev_addr, unsigned int value, void* stream);
+int ld_stream_wait_geq_u32(void* dev_addr, unsigned int value, void* stream);
+
 /* ---- fused memory-bound row kernels ------------------------------------------------------------------- */
 /* out = LayerNorm(x; w, b, eps) * (1 + scale[seg]) + shift[seg]   (dit_video_concat.py:577-586, 601-611, :388)
    x: bf16 or fp32 (x_is_f32) [B*rows_per_batch, D]; out: bf16; w,b: bf16 [D]; shift_x / scale_x: fp32 [D] of sample 0.

@@ -46,6 +46,13 @@ SIGNATURES = {
     "ld_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "ld_attention_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ld_attention_merge": (C.c_int, [_fp, _fp, _fp, _fp, _vp, _i, _i, _i, _vp]),
+    "ld_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
+    "ld_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "ld_ipc_close": (C.c_int, [_vp]),
+    "ld_ipc_free": (C.c_int, [_vp]),
+    "ld_copy_async": (C.c_int, [_vp, _vp, C.c_size_t, _vp]),
+    "ld_stream_write_u32": (C.c_int, [_vp, C.c_uint, _vp]),
+    "ld_stream_wait_geq_u32": (C.c_int, [_vp, C.c_uint, _vp]),
     "ld_layernorm_modulate": (C.c_int, [_vp, _i, _vp, _vp, _vp, _f, _fp, _fp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),
     "ld_final_norm_modulate": (C.c_int, [_vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),
     "ld_patchify": (C.c_int, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -98,10 +98,19 @@ def ring_attention_generic(q, kv_local, sp_size: int, sp_rank: int, exchange: Ca
 
 
 class RingAttention:
-    """GPU ring: attached to a DiffusionTransformer as `.ring`; called with the layer workspace."""
+    """GPU ring: attached to a DiffusionTransformer as `.ring`; called with the layer workspace.
 
-    def __init__(self, layout: Layout, sp_group, device):
+    transport "nccl" (default): batch_isend_irecv on a high-priority side stream.  transport "dma" (or
+    LD_RING_TRANSPORT=dma): copy-engine peer copies into IPC-mapped buffers ordered by stream memory operations
+    (landiff_b200/dma_ring.py) — no SMs, which matters because the attention kernel leaves none free."""
+
+    def __init__(self, layout: Layout, sp_group, device, transport: Optional[str] = None):
+        import os
+
         self.layout, self.group, self.device = layout, sp_group, device
+        self.transport = (transport or os.environ.get("LD_RING_TRANSPORT", "nccl")).lower()
+        if self.transport not in ("nccl", "dma"):
+            raise ValueError(f"unknown ring transport {self.transport!r}")
         # High priority: the attention kernel fills every SM (640 threads x ~100 registers), so NCCL's send/recv CTAs only
         # run when an SM drains; with priority they take the first free slots instead of queueing behind the
         # remaining attention CTAs (measured with the default priority: 34 MB hops at 129 GB/s, not hidden at sp = 4).
@@ -110,6 +119,7 @@ class RingAttention:
         self.next_rank = ranks[(layout.sp_rank + 1) % layout.sp_size]
         self.prev_rank = ranks[(layout.sp_rank - 1) % layout.sp_size]
         self._bufs = {}
+        self._peer = {}
 
     def _buffers(self, ws):
         key = id(ws)
@@ -118,12 +128,25 @@ class RingAttention:
             kv = ws["kv"]
             B, H, R = ws["q"].shape[:3]
             f = lambda *s: torch.empty(*s, dtype=torch.float32, device=kv.device)
-            b = dict(ring=[torch.empty_like(kv), torch.empty_like(kv)], o_acc=f(B * H, R, 64), lse_acc=f(B * H, R),
-                     o_new=f(B * H, R, 64), lse_new=f(B * H, R))
+            b = dict(o_acc=f(B * H, R, 64), lse_acc=f(B * H, R), o_new=f(B * H, R, 64), lse_new=f(B * H, R))
+            if self.transport == "nccl":
+                b["ring"] = [torch.empty_like(kv), torch.empty_like(kv)]
             self._bufs[key] = b
         return b
 
+    def _peer_ring(self, kv):
+        key = (tuple(kv.shape), kv.dtype)
+        pr = self._peer.get(key)
+        if pr is None:
+            from .dma_ring import PeerRing
+
+            pr = PeerRing(self.group, self.layout.sp_group_ranks(), self.layout.rank, kv.shape, kv.dtype, kv.device)
+            self._peer[key] = pr
+        return pr
+
     def attention(self, ws, variant: int = 0):
+        if self.transport == "dma":
+            return self._attention_dma(ws, variant)
         from . import ops
 
         sp = self.layout.sp_size
@@ -158,6 +181,56 @@ class RingAttention:
                 done.record(self.comm_stream)
                 compute.wait_event(done)
                 cur = nxt
+
+    def _attention_dma(self, ws, variant: int):
+        """Same schedule with the copy-engine transport: at hop h this rank forwards the shard it holds into the
+        downstream rank's recv[h % 2] while it attends to it; the shard for hop h+1 arrives in its own recv[h % 2]."""
+        from . import ops
+
+        sp = self.layout.sp_size
+        b = self._buffers(ws)
+        q, out = ws["q"], ws["attn"]
+        B, H, R = q.shape[:3]
+        kv = ws["kv"]
+        pr = self._peer_ring(kv)
+        compute = torch.cuda.current_stream()
+        cur, cur_j, cur_T = kv, -1, 0     # shard held at this hop; the recv buffer it lives in (-1: local kv)
+        for hop in range(sp):
+            sent_T = None
+            if hop < sp - 1:
+                j = hop % 2
+                if hop == 0:
+                    ready = torch.cuda.Event()
+                    ready.record(compute)        # local K|V written by the QKV GEMM
+                    self.comm_stream.wait_event(ready)
+                else:
+                    pr.wait_arrival(cur_j, cur_T, self.comm_stream)   # forward as soon as it has landed
+                sent_T = pr.push(cur, j, self.comm_stream)
+            if hop > 0:
+                pr.wait_arrival(cur_j, cur_T, compute)
+            if hop == 0:
+                ops.attention(q, cur[0], cur[1], out=out, lse=b["lse_acc"], out_f32=b["o_acc"], variant=variant)
+            else:
+                ops.attention(q, cur[0], cur[1], out=out, lse=b["lse_new"], out_f32=b["o_new"], variant=variant)
+                ops.attention_merge(b["o_acc"], b["lse_acc"], b["o_new"], b["lse_new"], out if hop == sp - 1 else None,
+                                    B, H, R)
+            if hop < sp - 1:
+                # the next shard to attend to arrives in my recv[hop % 2] with the same id my own push carries
+                # (every rank numbers its transfers identically)
+                nxt_j, nxt_T = hop % 2, sent_T
+            if hop > 0:
+                # recv[cur_j] has been read by the attention above AND (if forwarded) by the push on the comm stream
+                if hop < sp - 1:
+                    fwd = torch.cuda.Event()
+                    fwd.record(self.comm_stream)
+                    compute.wait_event(fwd)
+                pr.release(cur_j, cur_T, compute)
+            if hop < sp - 1:
+                cur, cur_j, cur_T = pr.recv[nxt_j], nxt_j, nxt_T
+        # the QKV GEMM of the next layer overwrites ws["kv"]: the push of hop 0 must have read it
+        done = torch.cuda.Event()
+        done.record(self.comm_stream)
+        compute.wait_event(done)
 
 
 class CFGGroup:

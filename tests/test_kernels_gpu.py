@@ -141,6 +141,30 @@ def test_attention_overflow_fixup(variant):
     report("   lse", lse, (torch.logsumexp(s, -1) * 1.4426950408889634).view(B * H, nq), 1e-5)
 
 
+@pytest.mark.parametrize("k0", [40.0, 90.0, 150.0])
+def test_attention_late_dominant_key_without_overflow(k0):
+    """A late key 25-110 log2-units above every row's first-block maximum: below the overflow limit, so the default
+    kernel keeps its fixed reference maximum (P up to 2^110) and must still match — floating point is scale-invariant."""
+    torch.manual_seed(6)
+    B, H, nq, nkv = 1, 2, 520, 2000
+    q = torch.randn(B, H, nq, 64, device=dev)
+    k = torch.randn(B, H, nkv, 64, device=dev)
+    v = torch.randn(B, H, nkv, 64, device=dev)
+    q[..., 0] = q[..., 0].abs() + 3.0
+    k[:, :, 1500, :] = 0
+    k[:, :, 1500, 0] = k0
+    k[:, :, 1700, :] = 0
+    k[:, :, 1700, 0] = k0 - 1.0       # a second, slightly weaker key so the result is not a single-row copy
+    q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    lse = torch.zeros(B * H, nq, device=dev)
+    out = ops.attention(q, k, v, lse=lse)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    report(f"attn dominant key {k0}", out, ref.permute(0, 2, 1, 3).reshape(B, nq, H * 64))
+    s = (q.float() @ k.float().transpose(-1, -2)) * 0.125
+    report("   lse", lse, (torch.logsumexp(s, -1) * 1.4426950408889634).view(B * H, nq), 1e-5)
+
+
 def test_row_kernels():
     torch.manual_seed(2)
     B, R, TL, D = 2, 443, 100, 1920
