@@ -138,10 +138,20 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, nq: Optional
     if out is None:
         out = torch.empty((B, nq, H * 64), dtype=BF16, device=q.device)
     _chk(out, BF16, "out")
+    if k.shape != v.shape or k.shape[:2] != q.shape[:2]:
+        raise ValueError(f"attention: q {tuple(q.shape)} / k {tuple(k.shape)} / v {tuple(v.shape)} do not agree")
+    if not (0 < nq <= q_rows and 0 < nkv <= kv_rows):
+        raise ValueError(f"attention: nq={nq} / nkv={nkv} outside the buffers ({q_rows} / {kv_rows} rows)")
+    if out.numel() != B * nq * H * 64:
+        raise ValueError(f"attention: out must hold [B, nq, H*64] = {B * nq * H * 64} elements, got {out.numel()}")
     if lse is not None:
         _chk(lse, F32, "lse")
+        if lse.numel() != B * H * nq:
+            raise ValueError("attention: lse must hold [B*H, nq] elements")
     if out_f32 is not None:
         _chk(out_f32, F32, "out_f32")
+        if lse is None or out_f32.numel() != B * H * nq * 64:
+            raise ValueError("attention: out_f32 must hold [B*H, nq, 64] elements and needs lse")
     check(_C.load().ld_attention_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _ptr(lse), _ptr(out_f32),
                                       B, H, nq, q_rows, nkv, kv_rows, variant, _stream()), "ld_attention_bf16")
     return out
