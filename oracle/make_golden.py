@@ -4,6 +4,10 @@ container.  Run:  python -m oracle.make_golden
 
   tests/golden/tiny_warp.pt     seeded (strong init, see ref_build.seeded_init_) TINY ControlDiffWarp pair: bf16-representable state dicts under the reference's
                                 key names, inputs, reference fp32 output + per-layer control hidden states
+  tests/golden/small_warp_b.pt  a second shape that exercises what TINY cannot: 3 control layers feeding a 5-layer main net
+                                (zero-linear chaining, control add only for i < control_layers), 3 heads, 3 latent frames,
+                                a text length that is not a multiple of anything, the SURVEY 8d "weak" init (N(0, 0.02^2))
+                                and a mid-range timestep; weights regenerated from the seed (not stored), outputs only
   tests/golden/schedule.json    ZeroSNRDDPMDiscretization(shift_scale=3) 50-step table + timesteps, the 1000-entry
                                 denoiser table (head/tail + checksum), DynamicCFG scales as the sampler calls it,
                                 DPM++(2M) SDE scalars for every step
@@ -74,6 +78,41 @@ def make_tiny_warp():
     print("tiny_warp.pt", (OUT / "tiny_warp.pt").stat().st_size, "bytes; out abs mean", out.abs().mean().item())
 
 
+SMALL_B = dict(hidden_size=192, num_heads=3, main_layers=5, control_layers=3, time_embed_dim=96, text_hidden=128,
+               text_length=7, latent_t=3, latent_h=6, latent_w=10)
+
+
+def small_b_inputs(cfg):
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, cfg.latent_t, 16, cfg.latent_h, cfg.latent_w, generator=g)
+    ctx = (torch.randn(2, cfg.text_length, cfg.text_hidden, generator=g) * 0.2).to(torch.bfloat16).float()
+    ctx[0] = 0
+    sem = (torch.randn(1, cfg.latent_t, 16, cfg.latent_h, cfg.latent_w, generator=g) * 0.1).to(torch.bfloat16).float()
+    return x, ctx, sem, torch.tensor([519.0, 519.0])
+
+
+def make_small_warp_b():
+    """Outputs of the reference modules for SMALL_B.  Weights are NOT stored: `ref_build.seeded_init_` draws them in
+    sorted-parameter-name order from one seeded generator, which `dit_oracle.seeded_state_dict` restates, so the test
+    regenerates bit-identical (bf16-rounded) parameters from the seed."""
+    cfg = rb.DiTConfig(**SMALL_B)
+    blob = {"cfg": SMALL_B, "seed": 5}
+    for strong, tag in ((False, "weak"), (True, "strong")):
+        ctrl, main = rb.build_reference(cfg, seed=5, strong=strong)
+        for m in (ctrl, main):
+            for p in m.parameters():
+                p.data.copy_(p.data.to(torch.bfloat16).float())
+        x, ctx, sem, t = small_b_inputs(cfg)
+        out, ctl = rb.reference_forward(ctrl, main, x, t, ctx, sem)
+        blob[tag] = {"out": out.float(), "control_hidden": [c["hidden_states"].float() for c in ctl],
+                     "probe": {k: ctrl.state_dict()[k].flatten()[:4].clone() for k in
+                               ("time_embed.0.weight", "mixins.adaln_layer.zero_linears.2.weight",
+                                "transformer.layers.1.attention.query_key_value.bias")}}
+        print(f"small_warp_b[{tag}] out abs mean", out.abs().mean().item())
+    torch.save(blob, OUT / "small_warp_b.pt")
+    print("small_warp_b.pt", (OUT / "small_warp_b.pt").stat().st_size, "bytes")
+
+
 def make_schedule():
     sampler, denoiser = reference_sampler(50)
     x = torch.zeros(1, 1, 1, 1, 1)
@@ -116,5 +155,6 @@ def make_sampler_toy():
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     make_tiny_warp()
+    make_small_warp_b()
     make_schedule()
     make_sampler_toy()
