@@ -12,7 +12,8 @@ container.  Run:  python -m oracle.make_golden
                                 denoiser table (head/tail + checksum), DynamicCFG scales as the sampler calls it,
                                 DPM++(2M) SDE scalars for every step
   tests/golden/sampler_toy.pt   5-step trajectory of the reference VPSDEDPMPP2MSampler + DiscreteDenoiser + DynamicCFG
-                                driving a toy analytic network (pins the sampler/denoiser/guider algebra + RNG order)
+                                driving a toy analytic network (pins the sampler/denoiser/guider algebra + RNG order),
+                                without and with fixed_frames=1 (the streaming prefix hook)
 """
 from __future__ import annotations
 
@@ -27,7 +28,7 @@ from . import sat_shim
 OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
 
 
-def reference_sampler(num_steps=50, device="cpu"):
+def reference_sampler(num_steps=50, device="cpu", fixed_frames=0):
     sat_shim.install()
     from landiff.diffusion.sgm.modules.diffusionmodules.denoiser import DiscreteDenoiser
     from landiff.diffusion.sgm.modules.diffusionmodules.sampling import VPSDEDPMPP2MSampler
@@ -35,7 +36,7 @@ def reference_sampler(num_steps=50, device="cpu"):
     disc = {"target": "landiff.diffusion.sgm.modules.diffusionmodules.discretizer.ZeroSNRDDPMDiscretization",
             "params": {"shift_scale": 3.0}}
     sampler = VPSDEDPMPP2MSampler(
-        num_steps=num_steps, verbose=False, device=device, discretization_config=disc,
+        num_steps=num_steps, verbose=False, device=device, discretization_config=disc, fixed_frames=fixed_frames,
         guider_config={"target": "landiff.diffusion.sgm.modules.diffusionmodules.guiders.DynamicCFG",
                        "params": {"scale": 6, "exp": 5, "num_steps": num_steps}})
     denoiser = DiscreteDenoiser(
@@ -147,9 +148,13 @@ def make_sampler_toy():
     torch.manual_seed(42)  # the sampler draws from the global generator (randn_like)
     den = lambda inp, sigma, c, **kw: denoiser(toy_network, inp, sigma, c, **kw)
     out = sampler(den, x0.clone(), cond, uc=uc)
-    torch.save({"x0": x0, "cond": cond["crossattn"], "uc": uc["crossattn"], "seed": 42, "num_steps": 5, "out": out},
-               OUT / "sampler_toy.pt")
-    print("sampler_toy.pt out abs mean", out.abs().mean().item())
+    # the same loop with a fixed 1-frame prefix (the streaming hook, sampling.py:800-817, 834-835)
+    sampler_ff, _ = reference_sampler(5, fixed_frames=1)
+    torch.manual_seed(42)
+    out_ff = sampler_ff(den, x0.clone(), cond, uc=uc)
+    torch.save({"x0": x0, "cond": cond["crossattn"], "uc": uc["crossattn"], "seed": 42, "num_steps": 5, "out": out,
+                "fixed_frames": 1, "out_fixed_frames": out_ff}, OUT / "sampler_toy.pt")
+    print("sampler_toy.pt out abs mean", out.abs().mean().item(), "with prefix", out_ff.abs().mean().item())
 
 
 if __name__ == "__main__":

@@ -100,6 +100,14 @@ def test_sampler_trajectory_toy_network():
     gen = torch.Generator().manual_seed(g["seed"])
     out = s(network, g["x0"].clone(), g["cond"], g["uc"], gen)
     assert rel(out, g["out"]) < 1e-6
+    # fixed_frames (streaming prefix): the prefix frames come back untouched, the rest follows the reference
+    s2 = O.OracleSampler(g["num_steps"], fixed_frames=g["fixed_frames"])
+    gen = torch.Generator().manual_seed(g["seed"])
+    out2 = s2(network, g["x0"].clone(), g["cond"], g["uc"], gen)
+    assert torch.equal(out2[:, :g["fixed_frames"]], g["x0"][:, :g["fixed_frames"]])
+    assert torch.equal(g["out_fixed_frames"][:, :g["fixed_frames"]], g["x0"][:, :g["fixed_frames"]])
+    assert rel(out2, g["out_fixed_frames"]) < 1e-6
+    assert rel(out2[:, :g["fixed_frames"]], g["out"][:, :g["fixed_frames"]]) > 1e-2   # without the hook they evolve
 
 
 @pytest.mark.parametrize("tag,strong", [("weak", False), ("strong", True)])
