@@ -447,7 +447,7 @@ constexpr int kAttn4Threads = 640;
 constexpr int kKS4 = 4;
 constexpr int kAttn4Smem = 2 * kKS4 * kTileBytes + 2 * 2 * 128 * 4 /* row-sum exchange */ + 1024 + 256;
 
-template <int POLY_EVERY, bool PROF>
+template <int POLY_EVERY, bool PROF, bool PACKED>
 __global__ void __launch_bounds__(kAttn4Threads, 1)
 attn4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
              const AttnParams p) {
@@ -672,29 +672,69 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__
       // ~100-clk round trips overlap the exponentials (both are almost always complete already).
       const bool pv_done = (i == 0) || mbar_test_wait(&o_done[t], (i - 1) & 1);
       s_ready = (i + 1 < n_sub) && mbar_test_wait(&s_full[2 * t + (b ^ 1)], ((i + 1) >> 1) & 1);
-      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
       uint32_t pk[16];
+      if constexpr (PACKED) {
+        // packed f32x2 FMA / ADD: same FMA-pipe throughput but half the issue slots for the scale-subtract and the row
+        // sums, which is what makes the polynomial split pay (tools/softmax_mix_bench.cu: 6.5 clk/element with every
+        // 4th exponential on the FMA pipe at 4 warps per SMSP, against 8.2 for the plain mix)
+        uint64_t sc2, nm2, sum01 = 0, sum23 = 0;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(sc2) : "f"(sl2));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(nm2) : "f"(-msc));
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float pv[4];
+        for (int c = 0; c < 8; ++c) {
+          uint64_t a01, a23;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(a01) : "r"(s[4 * c]), "r"(s[4 * c + 1]));
+          asm("mov.b64 %0, {%1, %2};" : "=l"(a23) : "r"(s[4 * c + 2]), "r"(s[4 * c + 3]));
+          asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a01) : "l"(sc2), "l"(nm2));
+          asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a23) : "l"(sc2), "l"(nm2));
+          float x[4], pv[4];
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(x[0]), "=f"(x[1]) : "l"(a01));
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(x[2]), "=f"(x[3]) : "l"(a23));
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int idx = 4 * c + e;
-          const float x = fmaf(__uint_as_float(s[idx]), sl2, -msc);
-          if constexpr (POLY_EVERY > 0) {
-            pv[e] = ((idx % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x) : ex2(x);
-          } else {
-            pv[e] = ex2(x);
+          for (int e = 0; e < 4; ++e) {
+            const int idx = 4 * c + e;
+            if constexpr (POLY_EVERY > 0) {
+              pv[e] = ((idx % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x[e]) : ex2(x[e]);
+            } else {
+              pv[e] = ex2(x[e]);
+            }
           }
+          uint64_t p01, p23;
+          asm("mov.b64 %0, {%1, %2};" : "=l"(p01) : "f"(pv[0]), "f"(pv[1]));
+          asm("mov.b64 %0, {%1, %2};" : "=l"(p23) : "f"(pv[2]), "f"(pv[3]));
+          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sum01) : "l"(p01));
+          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sum23) : "l"(p23));
+          pk[2 * c] = pack_bf16x2(pv[0], pv[1]);
+          pk[2 * c + 1] = pack_bf16x2(pv[2], pv[3]);
         }
-        sum0 += pv[0];
-        sum1 += pv[1];
-        sum2 += pv[2];
-        sum3 += pv[3];
-        pk[2 * c] = pack_bf16x2(pv[0], pv[1]);
-        pk[2 * c + 1] = pack_bf16x2(pv[2], pv[3]);
+        float s0, s1, s2, s3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(sum01));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(s2), "=f"(s3) : "l"(sum23));
+        l += (s0 + s1) + (s2 + s3);
+      } else {
+        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float pv[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int idx = 4 * c + e;
+            const float x = fmaf(__uint_as_float(s[idx]), sl2, -msc);
+            if constexpr (POLY_EVERY > 0) {
+              pv[e] = ((idx % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x) : ex2(x);
+            } else {
+              pv[e] = ex2(x);
+            }
+          }
+          sum0 += pv[0];
+          sum1 += pv[1];
+          sum2 += pv[2];
+          sum3 += pv[3];
+          pk[2 * c] = pack_bf16x2(pv[0], pv[1]);
+          pk[2 * c + 1] = pack_bf16x2(pv[2], pv[3]);
+        }
+        l += (sum0 + sum1) + (sum2 + sum3);
       }
-      l += (sum0 + sum1) + (sum2 + sum3);
       LD_PROF(3);
       if (!pv_done) mbar_wait(&o_done[t], (i - 1) & 1);   // PV(t,i-1) has consumed the P buffer
       LD_TMEM_ST16(tp_addr, pk);
@@ -804,10 +844,10 @@ static int launch_attn3(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
   return LD_OK;
 }
 
-template <int POLY_EVERY, bool PROF = false>
+template <int POLY_EVERY, bool PROF = false, bool PACKED = false>
 static int launch_attn4(const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& prm, int grid,
                         cudaStream_t st) {
-  auto kern = attn4_kernel<POLY_EVERY, PROF>;
+  auto kern = attn4_kernel<POLY_EVERY, PROF, PACKED>;
   static bool attr_set = false;
   if (!attr_set) {
     LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn4Smem));
@@ -889,7 +929,7 @@ extern "C" int ld_attention_bf16(const void* q, const void* k, const void* v, vo
   const int grid = BH * ((nq + 255) / 256);
   // variant 0: attn4_kernel (fixed first-block reference maximum) + exact fix-up launch   1: exact kernel only
   //         (attn3_kernel: per-block maxima, lazy rescaling)   2 / 3: attn4 with every 4th / 3rd exponential on the
-  //         FMA pipe (polynomial)
+  //         FMA pipe (polynomial)   4 / 5 / 6: attn4 with packed f32x2 FMA / ADD and every 4th / 8th / no polynomial
   cudaStream_t st = (cudaStream_t)stream;
   switch (variant) {
     case 1:
@@ -900,7 +940,10 @@ extern "C" int ld_attention_bf16(const void* q, const void* k, const void* v, vo
       return launch_attn3<0>(tq, tk, tv, prm, grid, st);
     case 0:
     case 2:
-    case 3: {
+    case 3:
+    case 4:
+    case 5:
+    case 6: {
       rc = redo_buffer(grid, &prm.redo);
       if (rc != LD_OK) return rc;
       if (variant == 0 && g_attn_prof != nullptr) {
@@ -910,8 +953,14 @@ extern "C" int ld_attention_bf16(const void* q, const void* k, const void* v, vo
         rc = launch_attn4<0>(tk, tv, prm, grid, st);
       } else if (variant == 2) {
         rc = launch_attn4<4>(tk, tv, prm, grid, st);
-      } else {
+      } else if (variant == 3) {
         rc = launch_attn4<3>(tk, tv, prm, grid, st);
+      } else if (variant == 4) {
+        rc = launch_attn4<4, false, true>(tk, tv, prm, grid, st);   // packed f32x2 + every 4th polynomial
+      } else if (variant == 5) {
+        rc = launch_attn4<8, false, true>(tk, tv, prm, grid, st);   // packed f32x2 + every 8th polynomial
+      } else {
+        rc = launch_attn4<0, false, true>(tk, tv, prm, grid, st);   // packed f32x2, all MUFU
       }
       if (rc != LD_OK) return rc;
       prm.prof = nullptr;

@@ -84,7 +84,8 @@ int ld_gemm_bf16(const ld_gemm_args* args, void* stream);
 /* q: [BH, q_rows, 64], k/v: [BH, kv_rows, 64] bf16; scores are scaled by 1/sqrt(64) inside the kernel.
    Uses q rows [0,nq) and kv rows [0,nkv).  out: bf16 [B, nq, heads*64] (token-major, ready for `dense`).
    variant: 0 = default (fixed per-row reference maximum + exact fix-up launch for overflowed CTAs), 1 = exact kernel
-   only (per-block maxima, lazy rescaling), 2 / 3 = default with every 4th / 3rd exponential as an FMA-pipe polynomial.
+   only (per-block maxima, lazy rescaling), 2 / 3 = default with every 4th / 3rd exponential as an FMA-pipe polynomial,
+   4 / 5 / 6 = default with packed f32x2 FMA / ADD and every 4th / 8th / no polynomial (experiments; slower today).
    Keeps one process-wide scratch array of per-CTA redo flags (allocated on first use), so concurrent calls must be
    on the same stream.
    If lse != NULL also writes fp32 log2-sum-exp [BH, nq] and, when out_f32 != NULL, the normalised fp32 output

@@ -96,7 +96,7 @@ def test_gemm_all_epilogues():
     report("gemm UNPATCHIFY", out, y.permute(0, 1, 4, 2, 5, 3, 6).reshape(B, T, Cc, 2 * Hp, 2 * Wp))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
 def test_attention(variant):
     torch.manual_seed(1)
     for (B, H, nq, nkv) in [(1, 1, 128, 128), (1, 1, 256, 128), (1, 2, 300, 300), (2, 3, 886, 886), (1, 2, 500, 1000),
@@ -116,7 +116,7 @@ def test_attention(variant):
         report("   out_f32", of, ref.reshape(B * H, nq, 64))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4])
 def test_attention_overflow_fixup(variant):
     """One late key whose score is hundreds of log2-units above every row's first-block maximum: the fixed reference
     maximum of attn4_kernel overflows, the CTA raises its redo flag and the exact kernel recomputes it.  Rows with a

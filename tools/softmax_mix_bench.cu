@@ -121,7 +121,7 @@ template <int CH, int POLY>
 void runp(const char* name, const float* in, uint32_t* out, unsigned long long* cyc) {
   printf("%-46s", name);
   const int iters = 2000;
-  for (int threads : {128, 256, 384}) {
+  for (int threads : {128, 256, 384, 512}) {
     kp<CH, POLY><<<148, threads>>>(in, out, cyc, 0.18f, 3.0f, iters);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf(" ERR %s", cudaGetErrorString(e)); continue; }
@@ -135,11 +135,79 @@ void runp(const char* name, const float* in, uint32_t* out, unsigned long long* 
   printf("\n");
 }
 
+// Candidate for the next attention iteration: packed f32x2 FMA / ADD (half the issue slots of the scale-subtract and
+// the row sums) with every POLY-th exponential as an FMA-pipe polynomial, 32 elements per visit like attn4_kernel.
+template <int POLY>
+__global__ void kx(const float* in, uint32_t* out, unsigned long long* cyc, float sl2, float msc, int iters) {
+  float s[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s[i] = in[threadIdx.x * 32 + i];
+  uint32_t acc = 0;
+  unsigned long long sum01 = 0, sum23 = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t pk[16];
+    unsigned long long sc, ms;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(sc) : "f"(sl2));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ms) : "f"(-msc));
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      unsigned long long a01, a23;
+      asm("mov.b64 %0, {%1, %2};" : "=l"(a01) : "f"(s[4 * c]), "f"(s[4 * c + 1]));
+      asm("mov.b64 %0, {%1, %2};" : "=l"(a23) : "f"(s[4 * c + 2]), "f"(s[4 * c + 3]));
+      asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a01) : "l"(sc), "l"(ms));
+      asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a23) : "l"(sc), "l"(ms));
+      float x[4], pv[4];
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(x[0]), "=f"(x[1]) : "l"(a01));
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(x[2]), "=f"(x[3]) : "l"(a23));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int idx = 4 * c + e;
+        pv[e] = (POLY > 0 && (idx % (POLY > 0 ? POLY : 1)) == POLY - 1) ? ex2_poly(x[e]) : ex2(x[e]);
+      }
+      unsigned long long p01, p23;
+      asm("mov.b64 %0, {%1, %2};" : "=l"(p01) : "f"(pv[0]), "f"(pv[1]));
+      asm("mov.b64 %0, {%1, %2};" : "=l"(p23) : "f"(pv[2]), "f"(pv[3]));
+      asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sum01) : "l"(p01));
+      asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sum23) : "l"(p23));
+      __nv_bfloat162 v0 = __floats2bfloat162_rn(pv[0], pv[1]);
+      __nv_bfloat162 v1 = __floats2bfloat162_rn(pv[2], pv[3]);
+      pk[2 * c] = *reinterpret_cast<uint32_t*>(&v0);
+      pk[2 * c + 1] = *reinterpret_cast<uint32_t*>(&v1);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc ^= pk[i];
+    msc += 1e-3f;
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc + (uint32_t)(sum01 ^ sum23);
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int POLY>
+void runx(const char* name, const float* in, uint32_t* out, unsigned long long* cyc) {
+  printf("%-46s", name);
+  const int iters = 4000;
+  for (int threads : {128, 256, 384, 512}) {
+    kx<POLY><<<148, threads>>>(in, out, cyc, 0.18f, 3.0f, iters);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf(" ERR %s", cudaGetErrorString(e)); continue; }
+    unsigned long long h[148];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double avg = 0;
+    for (int i = 0; i < 148; ++i) avg += h[i];
+    avg /= 148;
+    printf("  %dw/smsp: %6.2f cyc/elem/warp (%5.2f per SMSP)", threads / 128, avg / iters / 32, avg / iters / 32 / (threads / 128));
+  }
+  printf("\n");
+}
+
 template <int MODE>
 void run(const char* name, const float* in, uint32_t* out, unsigned long long* cyc) {
   printf("%-46s", name);
   const int iters = 2000;
-  for (int threads : {128, 256, 384}) {
+  for (int threads : {128, 256, 384, 512}) {
     k<MODE><<<148, threads>>>(in, out, cyc, 0.18f, 3.0f, iters);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf(" ERR %s", cudaGetErrorString(e)); continue; }
@@ -156,7 +224,7 @@ void run(const char* name, const float* in, uint32_t* out, unsigned long long* c
 int main() {
   float* in; uint32_t* out; unsigned long long* cyc;
   cudaMalloc(&in, 512 * 64 * 4); cudaMemset(in, 0, 512 * 64 * 4);
-  cudaMalloc(&out, 148 * 512 * 4); cudaMalloc(&cyc, 148 * 8);
+  cudaMalloc(&out, 148 * 512 * 4); cudaMalloc(&cyc, 148 * 8);   // in: 512 threads x 64 floats (zeroed)
   run<0>("ffma + ex2 + fadd + cvt.bf16x2/2", in, out, cyc);
   run<1>("ffma2 + ex2 + fadd + cvt.bf16x2/2", in, out, cyc);
   run<2>("ffma + ex2 + fadd (no pack)", in, out, cyc);
@@ -170,5 +238,10 @@ int main() {
   runp<16, 3>("pipelined by 16, every 3rd polynomial", in, out, cyc);
   runp<32, 4>("pipelined by 32, every 4th polynomial", in, out, cyc);
   runp<16, 2>("pipelined by 16, every 2nd polynomial", in, out, cyc);
+  runp<16, 8>("pipelined by 16, every 8th polynomial", in, out, cyc);
+  runx<0>("packed f32x2 fma/add, all MUFU (32/visit)", in, out, cyc);
+  runx<8>("packed f32x2 fma/add, every 8th polynomial", in, out, cyc);
+  runx<4>("packed f32x2 fma/add, every 4th polynomial", in, out, cyc);
+  runx<3>("packed f32x2 fma/add, every 3rd polynomial", in, out, cyc);
   return 0;
 }
