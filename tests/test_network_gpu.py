@@ -191,3 +191,21 @@ def test_full_shape_step_against_oracle_fp32_on_gpu():
     r, c = rel(out, ref), cos(out, ref)
     print(f"full shape (N=17776, 15+30 layers, B=2): rel-L2 {r:.3e} cos {c:.6f}; uncond/cond rows differ by {rel(out[0], out[1]):.3e}")
     assert r <= REL_TOL and c >= COS_TOL, f"rel-L2 {r:.3e} cos {c:.6f}"
+
+
+@pytest.mark.parametrize("tag,strong", [("weak", False), ("strong", True)])
+def test_small_warp_b_golden_from_reference_code(tag, strong):
+    """Second reference-generated golden (tests/golden/small_warp_b.pt): 3 control layers into a 5-layer main net,
+    d = 192 (3 heads), 3 latent frames, text length 7, timestep 519 — weights regenerated from the stored seed."""
+    from landiff_b200.factory import DiTShape
+    from oracle.make_golden import small_b_inputs
+
+    g = torch.load(GOLDEN / "small_warp_b.pt", weights_only=False)
+    cfg_o = O.OracleConfig(**g["cfg"])
+    sdc = O.seeded_state_dict(cfg_o, True, g["seed"], strong)
+    sdm = O.seeded_state_dict(cfg_o, False, g["seed"] + 1, strong)
+    warp = build_warp(DiTShape(**g["cfg"]), device="cuda", sd_ctrl=sdc, sd_main=sdm)
+    x, ctx, sem, t = small_b_inputs(cfg_o)
+    out = run_warp(warp, x, t, ctx, sem).float().cpu()
+    r, c = rel(out, g[tag]["out"]), cos(out, g[tag]["out"])
+    assert r <= REL_TOL and c >= COS_TOL, f"rel-L2 {r:.3e} cos {c:.6f}"
