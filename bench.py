@@ -249,28 +249,70 @@ def run_ours(args):
             "clocks": clk,
         }
         if world == 1:
-            line["cpu_baseline"] = cpu_baseline_sample(max_seconds=40)
+            line["cpu_baseline"] = cpu_baseline_sample()
+            if not args.no_eager:
+                eager = gpu_eager_baseline(warp, cfg, x_dev, torch.cat((uc["crossattn"], cond["crossattn"]), 0),
+                                           dit.InferValueRegistry.get_value("semantic_feature"))
+                eager["ours_over_eager"] = round(value / eager["value"], 4)
+                line["gpu_eager_baseline"] = eager
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-# ---------------------------------------------------------------------------------------------------- CPU side
-def cpu_baseline_sample(max_seconds=40, layers=None):
-    """The oracle port (plain PyTorch fp32, the reference module graph restated) on the host cores: one CFG step at
-    BASELINE config 1 (5 frames 240x352, N = 886 tokens), extrapolated to the full job by algorithmic FLOPs."""
-    import dataclasses
-
+# ---------------------------------------------------------------------------------------------------- B2: eager GPU
+def gpu_eager_baseline(warp, cfg, x_dev, ctx2, sem, steps=3):
+    """The reference module graph in PyTorch eager bf16 on the SAME GPU (cuBLAS GEMMs + F.scaled_dot_product_attention +
+    ~25 elementwise/norm launches per block) — SURVEY.md section 2.1's "B2" bar: what a user of the reference gets on a
+    B200 without this repo.  The graph is the oracle's restatement of dit_video_concat.py:540-664 / :872-1027 run on
+    the warp's own bf16 parameters (no copies); N = 1 only, outside the timed region of the product arm."""
     from oracle import dit_oracle as O
 
-    cores = os.cpu_count() or 1
+    sd = warp.state_dict()
+    pick = lambda prefix: {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+    sdc, sdm = pick("control_model.diffusion_model."), pick("main_model.diffusion_model.")
+    ocfg = O.OracleConfig(hidden_size=cfg.hidden_size, num_heads=cfg.num_heads, main_layers=cfg.main_layers,
+                          control_layers=cfg.control_layers, time_embed_dim=cfg.time_embed_dim, text_hidden=cfg.text_hidden,
+                          text_length=cfg.text_length, latent_t=cfg.latent_t, latent_h=cfg.latent_h, latent_w=cfg.latent_w,
+                          in_channels=cfg.in_channels, interp=cfg.interp)
+    x2 = torch.cat([x_dev, x_dev])
+    t2 = torch.full((2,), 519.0, device=x_dev.device)
+    run = lambda: O.warp_forward(sdc, sdm, ocfg, x2, t2, ctx2, sem)
+    run()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(x_dev.device.index or 0)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = run()
+    e1.record()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1) / steps
+    del out
+    torch.cuda.empty_cache()
+    return {"value": round(ms * SAMPLER_STEPS / 1e3, 4), "unit": UNIT, "ms_per_step": round(ms, 3), "steps_timed": steps,
+            "what": "reference module graph (oracle restatement), PyTorch eager bf16 on this GPU: cuBLAS + SDPA, same shape, "
+                    "CFG batch 2, network evaluation only (the eager sampler update adds < 0.2 ms)",
+            "clocks": clk}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU side
+CPU_THREADS = 16   # fixed thread count of the CPU legs (fewer if the box has fewer cores), so runs are comparable
+
+
+def cpu_baseline_sample():
+    """The oracle port (plain PyTorch fp32, the reference module graph restated) on the host cores: ONE full-depth
+    (15 + 30 layers, d = 1920) CFG step at BASELINE config 1 (5 frames 240x352, N = 886 tokens).  `value` extrapolates
+    that measurement to the full job (N = 17 776 tokens, 50 steps) by algorithmic FLOPs and is labelled as such: the CPU
+    cannot run the full shape within the bench's time budget (~10 min per step)."""
+    from oracle import dit_oracle as O
+
+    cores = min(CPU_THREADS, os.cpu_count() or 1)
     torch.set_num_threads(cores)
     cfg = O.CONFIG1
-    frac = 1.0
-    if layers is not None:
-        cfg = dataclasses.replace(cfg, main_layers=layers[0], control_layers=layers[1])
-        frac = (layers[0] + layers[1] * 1.033) / (30 + 15 * 1.033)
     sdc = O.cast_state_dict(O.random_state_dict(cfg, True, seed=10), torch.float32)
     sdm = O.cast_state_dict(O.random_state_dict(cfg, False, seed=11), torch.float32)
     g = torch.Generator().manual_seed(1)
@@ -281,37 +323,39 @@ def cpu_baseline_sample(max_seconds=40, layers=None):
     t0 = time.perf_counter()
     O.warp_forward(sdc, sdm, cfg, x, t, ctx, sem)
     dt = time.perf_counter() - t0
-    flop = FLOP_PER_CFG_STEP_CONFIG1 * frac
-    full_job = dt * (FLOP_PER_CFG_STEP_FULL / flop) * SAMPLER_STEPS
-    return {"value": round(full_job, 1), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"one CFG step (batch 2) of the oracle port at BASELINE config 1 (N=886 tokens, "
-                      f"{cfg.main_layers}+{cfg.control_layers} layers, fp32) took {dt:.2f} s on {cores} threads; "
-                      f"extrapolated to 50 full-shape steps by algorithmic FLOPs (x{FLOP_PER_CFG_STEP_FULL / flop:.1f} x 50)",
-            "sample_seconds": round(dt, 3), "sample_tflops": round(flop / dt / 1e12, 3)}
+    ratio = FLOP_PER_CFG_STEP_FULL / FLOP_PER_CFG_STEP_CONFIG1
+    return {"value": round(dt * ratio * SAMPLER_STEPS, 1), "unit": UNIT, "cores": cores, "kind": "port",
+            "extrapolated": True, "same_config": False,
+            "sample": f"one full-depth CFG step (batch 2, 15+30 layers, fp32) of the oracle port at BASELINE config 1 "
+                      f"(N=886 tokens) took {dt:.2f} s on {cores} threads; value = that x {ratio:.1f} (algorithmic FLOPs "
+                      f"of the full 17776-token step; ignores that attention grows quadratically) x 50 steps",
+            "sample_seconds": round(dt, 3), "sample_tflops": round(FLOP_PER_CFG_STEP_CONFIG1 / dt / 1e12, 3)}
 
 
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the reference itself needs the
-    un-vendored SwissArmyTransformer and cannot be installed offline).  Rank 0 only."""
+    un-vendored SwissArmyTransformer and cannot be installed offline).  Rank 0 only.  Every step is one MEASURED
+    full-depth config-1 CFG step; `value` is its FLOP-extrapolation to the default arm's job and says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    total = max(args.warmup, 0) + args.steps
-    layers = None if total <= 6 else ((6, 3) if total <= 30 else (2, 1))  # keep the whole run within a few minutes
     vals = []
-    for i in range(total):
-        r = cpu_baseline_sample(layers=layers)
+    for i in range(max(args.warmup, 0) + args.steps):
+        r = cpu_baseline_sample()
         if i >= args.warmup:
             vals.append(r)
     value = sum(v["value"] for v in vals) / len(vals)
+    secs = sum(v["sample_seconds"] for v in vals) / len(vals)
     last = vals[-1]
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(value / SAMPLER_STEPS * 1e3, 1),
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "same job as the default arm; each step = one bounded sample (see cpu_baseline.sample), "
-                                   "extrapolated by algorithmic FLOPs"},
+            "extrapolated": True, "same_config": False, "measured_step_seconds_config1": round(secs, 3),
+            "config": {"workload": "MEASURED: full-depth (15+30 layers, d=1920) CFG step of the oracle port at BASELINE "
+                                   "config 1 (N=886 tokens) on the host cores; value EXTRAPOLATES it to the default arm's job "
+                                   "(N=17776, 50 steps) by algorithmic FLOPs — indicative only, not the same job"},
             "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": last["cores"], "kind": "port",
-                             "sample": last["sample"]},
+                             "extrapolated": True, "sample": last["sample"]},
             "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -322,6 +366,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager bf16 GPU baseline leg (N = 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -68,19 +68,32 @@ def lib_path() -> Path:
     return _build.LIB_PATH
 
 
+ABI_VERSION = 2   # must equal ld_abi_version() of the loaded library (bumped whenever a signature or struct changes)
+
+
 def load() -> C.CDLL:
-    """Build (if stale/missing) and load the library; bind signatures.  Raises on any failure."""
+    """Build (if stale/missing) and load the library; bind signatures.  Raises on any failure.  The build step is a
+    cheap source-hash stamp check when the library is current; a library that was built from other sources (a stale
+    git-ignored .so carried over from an older snapshot) is rebuilt, and one that cannot be rebuilt (no nvcc) but
+    reports another ABI version is refused."""
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not path.exists():
+    try:
         path = _build.build()
+    except Exception:
+        path = _build.LIB_PATH
+        if not path.exists():
+            raise
     lib = C.CDLL(str(path))
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
         fn.restype = res
         fn.argtypes = args
+    got = lib.ld_abi_version()
+    if got != ABI_VERSION:
+        raise LanDiffB200Error(f"{path} reports ABI version {got}, the Python binding expects {ABI_VERSION}: "
+                               "stale library — rebuild with `python -m landiff_b200.build --force`")
     _lib = lib
     return lib
 

@@ -60,7 +60,10 @@ def load_engine_checkpoint(warp, path: str, strict: bool = True) -> Dict[str, to
     ckpt = torch.load(resolve_checkpoint_path(path), map_location="cpu", weights_only=False)
     module_state = ckpt["module"] if isinstance(ckpt, dict) and "module" in ckpt else ckpt
     warp_sd, sem_sd, _ = split_engine_state(module_state)
-    own = warp.state_dict()
+    # The control net's semantic conditioner is a reference-side submodule (or nn.Identity): its keys are not part of the
+    # DiT key contract checked here.  When a real conditioner is attached its tensors are loaded from `sem_sd` below.
+    own_all = warp.state_dict()
+    own = {k: v for k, v in own_all.items() if not k.startswith(SEMANTIC_PREFIX)}
     missing = [k for k in own if k not in warp_sd]
     unexpected = [k for k in warp_sd if k not in own]
     bad_shape = [f"{k}: checkpoint {tuple(warp_sd[k].shape)} vs module {tuple(own[k].shape)}"
@@ -74,6 +77,12 @@ def load_engine_checkpoint(warp, path: str, strict: bool = True) -> Dict[str, to
         for k, p in own.items():
             if k in warp_sd:
                 p.copy_(warp_sd[k].to(dtype=p.dtype))
+    cond = getattr(getattr(getattr(warp, "control_model", None), "diffusion_model", None), "semantic_conditioner", None)
+    if cond is not None and not isinstance(cond, torch.nn.Identity) and len(list(cond.state_dict().keys())) > 0:
+        res = cond.load_state_dict(sem_sd, strict=False)
+        if strict and (res.missing_keys or res.unexpected_keys):
+            raise KeyError(f"semantic conditioner tensors do not match: missing {res.missing_keys[:8]} "
+                           f"unexpected {res.unexpected_keys[:8]}")
     return sem_sd
 
 

@@ -472,10 +472,11 @@ class ControlDiffusionTransformer(DiffusionTransformer):
         kwargs.pop("semantic_video_frames", None)
         modules = kwargs.get("modules", {})
         super().__init__(*args, **kwargs)
-        # the semantic conditioner stays on reference code (out of scope); instantiate it only if given
+        # the semantic conditioner stays on reference code (out of scope); instantiate it only if given,
+        # with the keyword-only `dtype` the reference passes (dit_video_concat.py:926-928, condition.py:32-45)
         sc = modules.get("semantic_condition_config")
-        self.semantic_conditioner = instantiate_from_config(sc) if sc and sc.get("target") != "torch.nn.Identity" \
-            else nn.Identity()
+        self.semantic_conditioner = instantiate_from_config(sc, dtype=self.dtype) \
+            if sc and sc.get("target") != "torch.nn.Identity" else nn.Identity()
 
     def _semantic_feature(self, x):
         reg = _registry()

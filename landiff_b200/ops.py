@@ -277,28 +277,98 @@ _registered = False
 
 
 def register_torch_ops() -> None:
-    """Expose the C-ABI entry points as `torch.ops.landiff_b200.*` (thin custom ops over the ctypes calls)."""
+    """Expose every compute entry point of the C-ABI as `torch.ops.landiff_b200.*` (called at import, below).  The ops
+    are thin CUDA-dispatch-key wrappers over the same ctypes calls the modules in `dit.py` / `sampling.py` make; ops that
+    write into caller-owned storage declare it in their schema (`Tensor(a!)`)."""
     global _registered
     if _registered:
         return
     lib = torch.library.Library("landiff_b200", "DEF")
-    lib.define("attention(Tensor q, Tensor k, Tensor v, int variant=0) -> Tensor")
-    lib.define("linear(Tensor a, Tensor w, Tensor? bias, int epilogue=1) -> Tensor")
-    lib.define("sampler_update(Tensor x, Tensor net_u, Tensor net_c, Tensor? old_den, Tensor? eps, float c_skip, "
-               "float c_out, float cfg, float m1, float m2, float m3, float m4, float mn, int mode) -> (Tensor, Tensor)")
+    D = lib.define
+    D("attention(Tensor q, Tensor k, Tensor v, int variant=0) -> Tensor")
+    D("attention_lse(Tensor q, Tensor k, Tensor v, int variant=0) -> (Tensor, Tensor, Tensor)")
+    D("attention_merge(Tensor(a!) o_acc, Tensor(b!) lse_acc, Tensor o_new, Tensor lse_new, Tensor(c!)? out_bf16, "
+      "int batch, int heads, int nq) -> ()")
+    D("linear(Tensor a, Tensor w, Tensor? bias, int epilogue=1) -> Tensor")
+    D("linear_gated_residual(Tensor a, Tensor w, Tensor? bias, Tensor resid, Tensor gate_img, Tensor gate_txt, "
+      "Tensor? add2, int rows_per_batch, int tok_offset, int text_len, int mod_batch_stride) -> Tensor")
+    D("linear_qkv(Tensor a, Tensor w, Tensor bias, Tensor q_ln_w, Tensor q_ln_b, Tensor k_ln_w, Tensor k_ln_b, int heads, "
+      "int rows_per_batch, float ln_eps=1e-6) -> (Tensor, Tensor, Tensor)")
+    D("linear_bias_pos(Tensor a, Tensor w, Tensor bias, Tensor pos, Tensor(a!) out, int rows_per_batch, "
+      "int out_rows_per_batch, int out_row_offset, int tok_offset, int text_len) -> ()")
+    D("linear_unpatchify(Tensor a, Tensor w, Tensor bias, Tensor(a!) out, int rows_per_batch, int tok_offset, "
+      "int text_len, int T, int Hp, int Wp, int C) -> ()")
+    D("layernorm_modulate(Tensor x, Tensor w, Tensor b, float eps, Tensor shift_img, Tensor scale_img, Tensor shift_txt, "
+      "Tensor scale_txt, int mod_batch_stride, int batch, int rows_per_batch, int tok_offset, int text_len) -> Tensor")
+    D("final_norm_modulate(Tensor x, Tensor w1, Tensor b1, float eps1, Tensor w2, Tensor b2, float eps2, Tensor shift, "
+      "Tensor scale, int mod_batch_stride, int batch, int rows_per_batch, int tok_offset, int text_len) -> Tensor")
+    D("patchify(Tensor x, Tensor? sem, int g0=0, int n=-1) -> Tensor")
+    D("small_linear(Tensor x, Tensor w, Tensor? bias, int act_in=0, int act_out=0, bool round_bf16=True) -> Tensor")
+    D("timestep_embedding(Tensor t, int dim, float max_period=10000.0, bool round_bf16=True) -> Tensor")
+    D("sampler_update(Tensor x, Tensor net_u, Tensor net_c, Tensor? old_den, Tensor? eps, float c_skip, "
+      "float c_out, float cfg, float m1, float m2, float m3, float m4, float mn, int mode) -> (Tensor, Tensor)")
 
     def _attention(q, k, v, variant=0):
         return attention(q, k, v, variant=variant)
 
+    def _attention_lse(q, k, v, variant=0):
+        B, H, nq, _ = q.shape
+        lse = torch.empty((B * H, nq), dtype=F32, device=q.device)
+        of = torch.empty((B * H, nq, 64), dtype=F32, device=q.device)
+        return attention(q, k, v, variant=variant, lse=lse, out_f32=of), lse, of
+
+    def _attention_merge(o_acc, lse_acc, o_new, lse_new, out_bf16, batch, heads, nq):
+        attention_merge(o_acc, lse_acc, o_new, lse_new, out_bf16, batch, heads, nq)
+
     def _linear(a, w, bias, epilogue=1):
+        if epilogue not in (EPI_NONE, EPI_BIAS, EPI_BIAS_GELU):
+            raise ValueError("landiff_b200::linear handles epilogues NONE / BIAS / BIAS_GELU; see the other linear_* ops")
         return gemm(a, w, epilogue=epilogue, bias=bias)
+
+    def _linear_gated_residual(a, w, bias, resid, gate_img, gate_txt, add2, rows_per_batch, tok_offset, text_len,
+                               mod_batch_stride):
+        out = torch.empty_like(resid)
+        return gemm(a, w, epilogue=EPI_GATED_RESID, bias=bias, out=out, rows_per_batch=rows_per_batch, tok_offset=tok_offset,
+                    text_len=text_len, resid=resid, add2=add2, gate_img=gate_img, gate_txt=gate_txt,
+                    mod_batch_stride=mod_batch_stride)
+
+    def _linear_qkv(a, w, bias, q_ln_w, q_ln_b, k_ln_w, k_ln_b, heads, rows_per_batch, ln_eps=1e-6):
+        B = a.shape[0] // rows_per_batch
+        q = torch.empty((B, heads, rows_per_batch, 64), dtype=BF16, device=a.device)
+        k, v = torch.empty_like(q), torch.empty_like(q)
+        gemm(a, w, epilogue=EPI_QKV, bias=bias, rows_per_batch=rows_per_batch, qkv=(q, k, v),
+             qk_ln=(q_ln_w, q_ln_b, k_ln_w, k_ln_b), ln_eps=ln_eps, heads=heads)
+        return q, k, v
+
+    def _linear_bias_pos(a, w, bias, pos, out, rows_per_batch, out_rows_per_batch, out_row_offset, tok_offset, text_len):
+        gemm(a, w, epilogue=EPI_BIAS_POS, bias=bias, out=out, rows_per_batch=rows_per_batch,
+             out_rows_per_batch=out_rows_per_batch, out_row_offset=out_row_offset, tok_offset=tok_offset, text_len=text_len,
+             pos=pos)
+
+    def _linear_unpatchify(a, w, bias, out, rows_per_batch, tok_offset, text_len, T, Hp, Wp, C_):
+        gemm(a, w, epilogue=EPI_UNPATCHIFY, bias=bias, out=out, rows_per_batch=rows_per_batch, tok_offset=tok_offset,
+             text_len=text_len, patch_grid=(T, Hp, Wp, C_))
+
+    def _patchify(x, sem, g0=0, n=-1):
+        return patchify(x, sem, g0=g0, n=None if n < 0 else n)
 
     def _sampler_update(x, net_u, net_c, old_den, eps, c_skip, c_out, cfg, m1, m2, m3, m4, mn, mode):
         return sampler_update(x, net_u, net_c, old_den, eps, c_skip=c_skip, c_out=c_out, cfg=cfg, m1=m1, m2=m2, m3=m3,
-                              m4=m4, mn=mn, mode=mode)
+                              m4=m4, mn=mn, mode=mode, net_dtype=net_u.dtype)
 
-    lib.impl("attention", _attention, "CUDA")
-    lib.impl("linear", _linear, "CUDA")
-    lib.impl("sampler_update", _sampler_update, "CUDA")
+    for name, fn in (("attention", _attention), ("attention_lse", _attention_lse), ("attention_merge", _attention_merge),
+                     ("linear", _linear), ("linear_gated_residual", _linear_gated_residual), ("linear_qkv", _linear_qkv),
+                     ("linear_bias_pos", _linear_bias_pos), ("linear_unpatchify", _linear_unpatchify),
+                     ("layernorm_modulate", layernorm_modulate), ("final_norm_modulate", final_norm_modulate),
+                     ("patchify", _patchify), ("small_linear", small_linear), ("timestep_embedding", timestep_embedding),
+                     ("sampler_update", _sampler_update)):
+        lib.impl(name, fn, "CUDA")
     register_torch_ops._lib = lib  # keep alive
     _registered = True
+
+
+TORCH_OPS = ("attention", "attention_lse", "attention_merge", "linear", "linear_gated_residual", "linear_qkv",
+             "linear_bias_pos", "linear_unpatchify", "layernorm_modulate", "final_norm_modulate", "patchify", "small_linear",
+             "timestep_embedding", "sampler_update")
+
+register_torch_ops()

@@ -271,6 +271,18 @@ class CFGGroup:
             return buf[0:1], buf[1:2]
         t2 = torch.full((2,), timestep, dtype=torch.float32, device=x.device)
         net = network(torch.cat([x, x]), t2, {"crossattn": ctx2}, idx=t2, **kwargs)
+        if lay.sp_size > 1:
+            # ring SP without CFG parallelism: both rows live here, but only this rank's token shard of each was written
+            mask = getattr(network, "owned_latent_mask", None)
+            if mask is None:
+                raise RuntimeError("sequence-parallel network without `owned_latent_mask` (use landiff_b200.parallel.attach)")
+            own = mask(x)
+            if self._buf is None or self._buf.shape != net.shape or self._buf.dtype != net.dtype:
+                self._buf = torch.zeros(net.shape, dtype=net.dtype, device=net.device)
+            buf = self._buf
+            buf.copy_(torch.where(own, net, torch.zeros_like(net)))
+            dist.all_reduce(buf, group=self.group)
+            return buf[0:1], buf[1:2]
         return net[0:1], net[1:2]
 
 

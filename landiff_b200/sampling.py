@@ -220,6 +220,9 @@ class VPSDEDPMPP2MSampler:
             c_skip, c_out = float(aq), float(-((1 - aq ** 2) ** 0.5))
             cfg = self.guider.scale_schedule(None, total - timestep)
             if cfg_group is None:
+                if getattr(network, "owned_latent_mask", None) is not None:
+                    raise RuntimeError("this network is token-sharded (ring sequence parallel): its output must be assembled "
+                                       "across ranks — pass cfg_group=landiff_b200.parallel.CFGGroup(layout)")
                 t2 = torch.full((2,), timestep, dtype=torch.float32, device=x.device)
                 net = network(torch.cat([x, x]), t2, {"crossattn": ctx2}, idx=t2, **kwargs)
                 net_u, net_c = net[0:1], net[1:2]

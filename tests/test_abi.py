@@ -27,7 +27,7 @@ def test_header_symbols_all_exported():
 
 def test_abi_version_and_struct_layout():
     lib = _C.load()
-    assert lib.ld_abi_version() == 1
+    assert lib.ld_abi_version() == _C.ABI_VERSION
     # ctypes mirror: natural alignment, pointer fields 8-aligned
     assert ctypes.sizeof(_C.GemmArgs) % 8 == 0
     for name in ("A", "W", "bias", "out", "resid", "q", "pos"):

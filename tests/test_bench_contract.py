@@ -22,6 +22,9 @@ def test_reference_arm_json_line():
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the CPU arm measures a config-1 step and says that its value is an extrapolation, not the same job
+    assert d["extrapolated"] is True and d["same_config"] is False and d["measured_step_seconds_config1"] > 0
+    assert "15+30 layers" in d["config"]["workload"] and d["cpu_baseline"]["cores"] <= 16
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

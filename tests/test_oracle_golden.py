@@ -134,3 +134,38 @@ def test_small_warp_b_golden(tag, strong):
     # the control branch matters in this golden: dropping it changes the output far beyond the tolerance
     no_ctrl = O.main_forward(O.cast_state_dict(sdm, torch.float32), cfg, x, t, ctx, None)
     assert ((no_ctrl - g[tag]["out"]).norm() / g[tag]["out"].norm()).item() > 1e-2
+
+
+@pytest.mark.parametrize("tag,strong", [("weak", False), ("strong", True)])
+def test_config1_real_width_golden_from_reference_modules(tag, strong):
+    """d = 1920, 30 heads, N = 886 (BASELINE config 1; `weak`: the full 15 + 30 layers): the oracle restatement against the
+    output of the reference's own ControlDiffusionTransformer -> DiffusionTransformer (oracle/make_config1_golden.py)."""
+    import dataclasses
+
+    gold = torch.load(GOLDEN / "config1_ref.pt", weights_only=False)[tag]
+    cfg = dataclasses.replace(O.CONFIG1, main_layers=gold["main_layers"], control_layers=gold["control_layers"])
+    sdc = O.cast_state_dict(O.random_state_dict(cfg, True, seed=10, strong=strong), torch.float32)
+    sdm = O.cast_state_dict(O.random_state_dict(cfg, False, seed=11, strong=strong), torch.float32)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, cfg.latent_t, 16, cfg.latent_h, cfg.latent_w, generator=g)
+    ctx = (torch.randn(2, cfg.text_length, cfg.text_hidden, generator=g) * 0.2).bfloat16().float()
+    ctx[0] = 0
+    sem = (torch.randn(1, cfg.latent_t, 16, cfg.latent_h, cfg.latent_w, generator=g) * 0.1).bfloat16().float()
+    out, ctl = O.warp_forward(sdc, sdm, cfg, x, torch.tensor([519.0, 519.0]), ctx, sem, return_control=True)
+    r = ((out - gold["out"]).norm() / gold["out"].norm()).item()
+    rc = ((ctl[-1][:, ::37] - gold["control_last"]).norm() / gold["control_last"].norm()).item()
+    assert r < 2e-5 and rc < 2e-5, f"oracle vs reference modules at config 1 [{tag}]: rel-L2 {r:.3e} / control {rc:.3e}"
+
+
+def test_oracle_trajectory_equals_reference_object_trajectory():
+    """The oracle's own 50-step config-1 trajectory (trajectory50_config1.pt, OracleSampler driving the oracle network)
+    against the trajectory the REFERENCE sampler + denoiser + guider + network objects produced from the same seeds
+    (trajectory50_config1_ref.pt): the restatement of the whole sampling loop is pinned at the real width and depth."""
+    a = torch.load(GOLDEN / "trajectory50_config1.pt", weights_only=False)
+    b = torch.load(GOLDEN / "trajectory50_config1_ref.pt", weights_only=False)
+    assert sorted(a["steps"]) == sorted(b["steps"])
+    for i in a["steps"]:
+        r = ((a["steps"][i] - b["steps"][i]).norm() / b["steps"][i].norm()).item()
+        assert r < 1e-3, f"step {i + 1}: oracle vs reference trajectory rel-L2 {r:.3e}"
+    r = ((a["final"] - b["final"]).norm() / b["final"].norm()).item()
+    assert r < 1e-3, f"final latent: oracle vs reference trajectory rel-L2 {r:.3e}"

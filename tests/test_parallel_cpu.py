@@ -111,7 +111,23 @@ def _worker(rank, world, port, ret):
         rows = torch.randn(2, 3, 4, 6, 8)
         buf = grp.assemble(rows[lay.cfg_rank:lay.cfg_rank + 1], lay.cfg_rank)
         err_c = (buf - rows).abs().max().item()
-        ret[rank] = (err, err_l, err_c)
+        # --- ring SP WITHOUT CFG parallelism: evaluate() must assemble both rows from the ranks' token shards
+        lay1 = P.make_layout(world, rank, cfg_parallel=False)
+        assert (lay1.cfg_size, lay1.sp_size) == (1, world)
+        T, C, Hh, Ww, TL = 2, 4, 4, 6, 4
+        n_tok = TL + T * (Hh // 2) * (Ww // 2)
+        s0, cnt = P.shard_bounds(n_tok, world, rank)
+        own = P.owned_latent_mask((T, C, Hh, Ww), TL, s0, cnt, "cpu")
+        x = torch.randn(1, T, C, Hh, Ww)
+
+        def sharded_net(x2, t2, c, idx=None):
+            full = x2 * 2.0 + t2.view(-1, 1, 1, 1, 1)
+            return torch.where(own, full, torch.full_like(full, float("nan")))   # rows outside the shard: garbage
+
+        sharded_net.owned_latent_mask = lambda xx: own
+        u, c_ = P.CFGGroup(lay1).evaluate(sharded_net, x, 5.0, torch.zeros(2, 3, 8))
+        err_sp = max((u - (x * 2 + 5)).abs().max().item(), (c_ - (x * 2 + 5)).abs().max().item())
+        ret[rank] = (err, err_l, err_c, err_sp)
     finally:
         dist.destroy_process_group()
 
@@ -124,6 +140,7 @@ def test_ring_and_cfg_exchange_gloo_world2():
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert len(ret) == world
     for r in range(world):
-        err, err_l, err_c = ret[r]
+        err, err_l, err_c, err_sp = ret[r]
+        assert err_sp == 0.0, f"rank {r}: SP-only output assembly wrong ({err_sp})"
         assert err < 1e-5 and err_l < 1e-5, f"rank {r}: ring attention differs from monolithic ({err}, {err_l})"
         assert err_c == 0.0, f"rank {r}: CFG assembly not exact"

@@ -10,6 +10,8 @@ using namespace ld;
 
 // MODE 0: SS only; 1: TS only (B N-major); 2: attention pattern: 4 x SS(N=64) then 4 x TS(N=64) alternating
 // MODE 3: TS with K-major B; 4: attn4 pattern: 4 x TS(K-major B) then 4 x TS(N-major B)
+// MODE 5 (round 2, attn5 pattern): per group of 12: 4 x TS(K-major B, N) [S], 4 x TS(N-major B, N) [PV], 4 x TS(K-major B,
+//         N = 16 against a ones tile) [row sums]; MODE 6: the same with the row-sum MMAs folded into PV as N + 16 (N-major)
 template <int N, int MODE, int NACC, int COMMIT_EVERY>
 __global__ void __launch_bounds__(128, 1) k(long long* out, int total) {
   extern __shared__ uint8_t smem_raw[];
@@ -33,6 +35,23 @@ __global__ void __launch_bounds__(128, 1) k(long long* out, int total) {
       const uint32_t d = tm + (g % NACC) * N;
       const bool ts = MODE == 1 || (MODE == 2 && (g & 1)) || (MODE == 4 && (g & 1));
       const bool tsk = MODE == 3 || (MODE == 4 && !(g & 1));
+      if (MODE == 5 || MODE == 6) {
+        constexpr uint32_t idesc_l = make_idesc_bf16(128, 16, false, false);
+        constexpr uint32_t idesc_pvl = make_idesc_bf16(128, N + 16, false, true);
+        if (leader) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_ts(tm + (g & 1) * 64, tm + 416 + ks * 8, bdesc + 2 * ks, idesc_ss, 1);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ts(tm + 256, tm + 128 + (g & 1) * 64 + ks * 8, bdesc + 128 * ks, MODE == 6 ? idesc_pvl : idesc_ts, 1);
+          if (MODE == 5) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_ts(tm + 384, tm + 128 + (g & 1) * 64 + ks * 8, adesc, idesc_l, 1);
+          }
+          if (COMMIT_EVERY) umma_commit(&bar[1]);
+        }
+        continue;
+      }
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -58,7 +77,7 @@ void run(long long* out) {
   const int total = 1024;
   auto kern = k<N, MODE, NACC, COMMIT_EVERY>;
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  printf("N=%3d %-4s acc=%d commit/%d groups |", N, MODE == 0 ? "SS" : MODE == 1 ? "TS" : MODE == 2 ? "S+TS" : MODE == 3 ? "TSk" : "TSk+TS", NACC, COMMIT_EVERY);
+  printf("N=%3d %-4s acc=%d commit/%d groups |", N, MODE == 0 ? "SS" : MODE == 1 ? "TS" : MODE == 2 ? "S+TS" : MODE == 3 ? "TSk" : MODE == 4 ? "TSk+TS" : MODE == 5 ? "S+PV+L16 (x/4: per group of 4 dispatched)" : "S+PV(N+16)", NACC, COMMIT_EVERY);
   for (int grid : {148, 1}) {
     kern<<<grid, 128, 100 * 1024>>>(out, total);
     cudaError_t e = cudaDeviceSynchronize();
@@ -85,5 +104,7 @@ int main() {
   run<64, 0, 2, 1>(out);  run<64, 2, 4, 1>(out);  run<128, 0, 2, 1>(out); run<192, 0, 2, 4>(out);
   run<32, 0, 2, 0>(out);  run<16, 0, 2, 0>(out);
   run<64, 3, 1, 0>(out);  run<64, 3, 2, 0>(out);  run<128, 3, 2, 0>(out);  run<64, 4, 4, 1>(out);
+  run<16, 3, 2, 0>(out);  run<32, 3, 2, 0>(out);   // TS-mode dispatch floor at small N (row-sum MMA against a ones tile)
+  run<64, 5, 1, 1>(out);  run<64, 6, 1, 1>(out);   // cycles are per counted MMA (4 per group): x4 = per 64-key sub-block
   return 0;
 }

@@ -203,6 +203,94 @@ void runx(const char* name, const float* in, uint32_t* out, unsigned long long* 
   printf("\n");
 }
 
+// Round-2 candidate (attn5): NO per-element FADD (the row sum comes from a tcgen05.mma against a ones tile), packed f32x2
+// scale-subtract, KP of every 16 element PAIRS exponentiated by a packed f32x2 polynomial on the FMA pipe (the rest on
+// MUFU), bf16 pack by F2FP (TRUNC = 0) or by a byte permute of the two high halves (TRUNC = 1; the truncation bias
+// cancels because the row sum is taken from the same truncated values).
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r;
+}
+__device__ __forceinline__ void ex2_poly2(unsigned long long x2, float& p0, float& p1) {
+  float x0, x1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x2));
+  x0 = fminf(fmaxf(x0, -127.0f), 128.0f);
+  x1 = fminf(fmaxf(x1, -127.0f), 128.0f);
+  const unsigned long long xc = pack2(x0, x1), magic = pack2(12582912.0f, 12582912.0f), nmagic = pack2(-12582912.0f, -12582912.0f);
+  unsigned long long xr, t, f, p;
+  asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(xr) : "l"(xc), "l"(magic));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(xr), "l"(nmagic));
+  const unsigned long long m1 = pack2(-1.0f, -1.0f);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(f) : "l"(t), "l"(m1), "l"(xc));
+  const unsigned long long c3 = pack2(0.077119089663028717f, 0.077119089663028717f), c2 = pack2(0.227564394474029541f, 0.227564394474029541f),
+                           c1 = pack2(0.695146143436431885f, 0.695146143436431885f), c0 = pack2(1.0f, 1.0f);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(f), "l"(c3), "l"(c2));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "+l"(p) : "l"(p), "l"(f), "l"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "+l"(p) : "l"(p), "l"(f), "l"(c0));
+  float q0, q1, r0, r1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(q0), "=f"(q1) : "l"(p));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(xr));
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
+}
+
+template <int KP, int TRUNC>
+__global__ void ky(const float* in, uint32_t* out, unsigned long long* cyc, float sl2, float msc, int iters) {
+  float s[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s[i] = in[threadIdx.x * 32 + i];
+  uint32_t acc = 0;
+  __syncthreads();
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t pk[16];
+    const unsigned long long sc = pack2(sl2, sl2), ms = pack2(-msc, -msc);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      unsigned long long a = pack2(s[2 * c], s[2 * c + 1]);
+      asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a) : "l"(sc), "l"(ms));
+      float p0, p1;
+      // pairs c with (c * KP) % 16 < KP go to the polynomial: KP pairs of 16, evenly spread
+      if (KP > 0 && ((c * KP) % 16) < KP) {
+        ex2_poly2(a, p0, p1);
+      } else {
+        float x0, x1;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(a));
+        p0 = ex2(x0); p1 = ex2(x1);
+      }
+      if (TRUNC) {
+        asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(pk[c]) : "r"(__float_as_uint(p0)), "r"(__float_as_uint(p1)));
+      } else {
+        __nv_bfloat162 v = __floats2bfloat162_rn(p0, p1);
+        pk[c] = *reinterpret_cast<uint32_t*>(&v);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc ^= pk[i];
+    msc += 1e-3f;
+  }
+  long long t1 = clock64();
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int KP, int TRUNC>
+void runy(const char* name, const float* in, uint32_t* out, unsigned long long* cyc) {
+  printf("%-46s", name);
+  const int iters = 4000;
+  for (int threads : {128, 256, 384, 512}) {
+    ky<KP, TRUNC><<<148, threads>>>(in, out, cyc, 0.18f, 3.0f, iters);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf(" ERR %s", cudaGetErrorString(e)); continue; }
+    unsigned long long h[148];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double avg = 0;
+    for (int i = 0; i < 148; ++i) avg += h[i];
+    avg /= 148;
+    printf("  %dw/smsp: %6.2f cyc/elem/warp (%5.2f per SMSP)", threads / 128, avg / iters / 32, avg / iters / 32 / (threads / 128));
+  }
+  printf("\n");
+}
+
 template <int MODE>
 void run(const char* name, const float* in, uint32_t* out, unsigned long long* cyc) {
   printf("%-46s", name);
@@ -243,5 +331,14 @@ int main() {
   runx<8>("packed f32x2 fma/add, every 8th polynomial", in, out, cyc);
   runx<4>("packed f32x2 fma/add, every 4th polynomial", in, out, cyc);
   runx<3>("packed f32x2 fma/add, every 3rd polynomial", in, out, cyc);
+  runy<0, 0>("r2: ffma2 + ex2 + cvt, no fadd, 0/16 poly", in, out, cyc);
+  runy<4, 0>("r2: no fadd, 4/16 pairs packed poly", in, out, cyc);
+  runy<5, 0>("r2: no fadd, 5/16 pairs packed poly", in, out, cyc);
+  runy<6, 0>("r2: no fadd, 6/16 pairs packed poly", in, out, cyc);
+  runy<8, 0>("r2: no fadd, 8/16 pairs packed poly", in, out, cyc);
+  runy<0, 1>("r2: no fadd, 0/16 poly, prmt pack", in, out, cyc);
+  runy<5, 1>("r2: no fadd, 5/16 poly, prmt pack", in, out, cyc);
+  runy<6, 1>("r2: no fadd, 6/16 poly, prmt pack", in, out, cyc);
+  runy<8, 1>("r2: no fadd, 8/16 poly, prmt pack", in, out, cyc);
   return 0;
 }
