@@ -137,20 +137,23 @@ def run_ours(args):
 
     # attention-kernel timing hook (the dominant kernel): CUDA events on the launch stream around each launch
     attn_events = []
-    orig_attention = ops.attention
 
-    def timed_attention(*a, **k):
-        if not timed_attention.on:
-            return orig_attention(*a, **k)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        r = orig_attention(*a, **k)
-        e.record()
-        attn_events.append((s, e))
-        return r
+    def timed(orig):
+        def f(*a, **k):
+            if not timed.on:
+                return orig(*a, **k)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig(*a, **k)
+            e.record()
+            attn_events.append((s, e))
+            return r
+        return f
 
-    timed_attention.on = False
-    ops.attention = timed_attention
+    timed.on = False
+    ops.attention = timed(ops.attention)                  # single-buffer launch (1 and 2 GPUs)
+    ops.attention_shards = timed(ops.attention_shards)    # multi-shard launch of the sequence-parallel layouts
+    timed_attention = timed
 
     def barrier():
         if world > 1:
@@ -216,7 +219,7 @@ def run_ours(args):
         # dominant kernel: attention.  algorithmic FLOPs per launch = 4 * nq * nkv * 64 * (B*H) for this rank's launch
         b_rows = 2 if layout.cfg_size == 1 else 1
         nq = cfg.n_tok // layout.sp_size
-        flop_per_launch = 4.0 * nq * nq * 64 * b_rows * cfg.num_heads
+        flop_per_launch = 4.0 * nq * cfg.n_tok * 64 * b_rows * cfg.num_heads   # this rank's queries x ALL keys (one launch)
         attn_avg = sum(attn_ms) / max(len(attn_ms), 1)
         # DRAM traffic of one attention launch from the `ncu --set full` capture of the same kernel and shape at B = 1
         # (profiles/r1_ncu_attn4.csv: dram__bytes_read.sum 205.7 MB + dram__bytes_write.sum 51.6 MB); the launch is
@@ -235,7 +238,9 @@ def run_ours(args):
                        "l2": "per-step working set (>6 GB) exceeds the 126 MB L2; no explicit flush",
                        "weights": "seeded random init N(0, 0.02^2)", "sampler_steps_per_video": SAMPLER_STEPS},
             "tensor_frac_of_peak_whole_step": round(FLOP_PER_CFG_STEP_FULL / (ms_per_step * 1e-3) / world / 1e12 / tf_peak, 4),
-            "roofline": {"bound": "tensor", "kernel": "attn4_kernel (tcgen05 flash attention, head_dim 64: double-buffered scores, 16 softmax warps, Q in TMEM)",
+            "roofline": {"bound": "tensor", "kernel": "attn5_kernel (tcgen05 flash attention, head_dim 64: double-buffered scores, 16 softmax warps, Q in "
+                                   "TMEM, P in place over S, row sums on the tensor core, 5/16 exponential pairs on the FMA pipe"
+                                   + ("" if layout.sp_size == 1 else f"; one launch over {layout.sp_size} K/V shards, arrival flags polled in-kernel") + ")",
                          "achieved": round(achieved, 1), "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": round(achieved / tf_peak, 4), "traffic": traffic,
                          "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r1_ncu_attn4.csv)",

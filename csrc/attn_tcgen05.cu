@@ -1,16 +1,22 @@
-// Full (non-causal) self-attention for head_dim 64 on sm_100a: flash-style online softmax with both
-// contractions on tcgen05 tensor cores and Q / S / P / O resident in TMEM.  Replaces
-// F.scaled_dot_product_attention as reached from dit_video_concat.py:655-664 (SAT attention_fn_default).
+// Full (non-causal) self-attention for head_dim 64 on sm_100a: flash-style online softmax with both contractions on
+// tcgen05 tensor cores and Q / S / P / O / row sums resident in TMEM.  Replaces F.scaled_dot_product_attention as
+// reached from dit_video_concat.py:655-664 (SAT attention_fn_default).
 //
-// Two kernels (history and measurements: DESIGN.md section 3a):
-//   attn4_kernel   the product path: per CTA 256 query rows as two 128-row tiles, double-buffered 64-key score
-//                  blocks, 16 softmax warps in column-split pairs, Q in TMEM (TS-mode S = Q K^T), two MMA issuer
-//                  warps, one fixed reference maximum per row (first sub-block) with overflow detection.
-//   attn3_kernel   the exact kernel (per-block maxima, lazy rescaling, four independent softmax streams); launched
-//                  after attn4_kernel to recompute only the CTAs that flagged an overflow, and on its own as
-//                  variant 1.
+// K/V may arrive as up to four SHARDS (ring sequence parallelism: the local shard plus the peers' shards that the copy
+// engines drop into IPC-mapped receive buffers): one launch walks all of them, accumulating in TMEM, and its TMA
+// producer warp polls a per-shard arrival flag before the first load from a shard that is still in flight — no
+// per-hop launches, no partial-result merges.
+//
+// One kernel, two code paths (history and measurements: DESIGN.md section 3a):
+//   fast path   per CTA 256 query rows as two 128-row tiles, double-buffered 64-key score blocks, 16 softmax warps in
+//               column-split pairs, Q in TMEM (TS-mode S = Q K^T), P written in place over S, row sums accumulated by
+//               the tensor core (P x ones), a fraction of the exponentials on the FMA pipe (packed f32x2 polynomial),
+//               ONE fixed reference maximum per row (first sub-block) with overflow detection.
+//   exact path  per-block maxima with lazy rescaling, four independent softmax streams.  Runs in the SAME launch for
+//               the (rare) CTAs whose fixed reference maximum overflowed, and on its own as variant 1.
 // K/V tail columns are masked to -inf; TMA zero-fills out-of-range rows.
 #include <cstdlib>
+#include <cstring>
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -19,20 +25,109 @@ namespace ld {
 using bf16 = __nv_bfloat16;
 
 constexpr int kTileBytes = 128 * 64 * 2;     // 16 KB: one 128x64 bf16 box
-constexpr float kRescaleThreshold = 8.0f;    // log2 units (attn3_kernel's lazy rescaling)
+constexpr float kRescaleThreshold = 8.0f;    // log2 units (exact path's lazy rescaling)
+constexpr int kMaxShards = 4;
+constexpr int kMaxSub = 2048;                // 64-key sub-blocks per launch: up to 131 072 keys over all shards
+constexpr int kKS = 4;                       // K and V ring depth (128-key boxes)
+constexpr int kAttnThreads = 640;
+
+struct alignas(64) AttnShards {
+  CUtensorMap q;                         // [64, nq, BH], box 64 x 128 (exact path)
+  CUtensorMap k[kMaxShards];             // [64, nkv_s, BH], box 64 x 128
+  CUtensorMap v[kMaxShards];
+  const uint32_t* ready[kMaxShards];     // arrival flag of shard s (null: already present): wait until
+  uint32_t ready_val[kMaxShards];        //   (int32)(*ready[s] - ready_val[s]) >= 0   (acquire, system scope)
+  int nkv[kMaxShards];
+  int n;                                 // shards
+  int n_sub;                             // 64-key sub-blocks over all shards
+  uint32_t* status;                      // [0] |= 1 when a shard wait gave up after wait_cycles (result invalid)
+  long long wait_cycles;
+};
 
 struct AttnParams {
   bf16* out;        // [B, nq, heads*64]
   float* lse;       // [BH, nq] or null
   float* out_f32;   // [BH, nq, 64] or null
-  int heads, nq, nkv;
+  int heads, nq;
   float scale_log2;
-  const bf16* q;     // [BH, q_rows, 64] (attn4_kernel reads Q rows directly)
+  const bf16* q;     // [BH, q_rows, 64] (the fast path reads Q rows directly)
   int q_rows;
-  int* redo;         // [grid] attn4_kernel: 1 = recompute this CTA with the exact kernel
-  int redo_only;     // attn3_kernel: run only the CTAs with redo[cta] != 0
-  long long* prof;   // per-(CTA, warp) phase cycle counters (profiling variants only)
+  int exact_only;    // variant 1: run the exact path for every CTA
+  long long* prof;   // per-(CTA, warp) phase cycle counters (profiling build of the fast path only)
 };
+
+// dynamic shared memory (1024-byte aligned base)
+constexpr int kOffK = 0;
+constexpr int kOffV = kOffK + kKS * kTileBytes;
+constexpr int kOffQ = kOffV + kKS * kTileBytes;          // exact path: two 128-row Q tiles
+constexpr int kOffOnes = kOffQ + 2 * kTileBytes;         // 16 rows x 128 B of bf16 1.0 (B operand of the row-sum MMA)
+constexpr int kOffTab = kOffOnes + 2048;                 // sub-block table
+constexpr int kOffML = kOffTab + kMaxSub * 4;            // exact path: (m, l) exchange, float2 [4][128]
+constexpr int kOffBarsFast = kOffML + 4 * 128 * 8;
+constexpr int kOffBarsExact = kOffBarsFast + 32 * 8;
+constexpr int kOffSlot = kOffBarsExact + 32 * 8;
+constexpr int kAttnSmem = kOffSlot + 16 + 1024 /* alignment slack */;
+
+// Sub-block table entry: box index (20 bits) | half of the box << 20 | last sub-block of its box << 21 | valid keys << 24.
+// Shards are walked box by box (128 keys per TMA box, two 64-key sub-blocks); a shard whose key count is not a multiple
+// of 128 ends with a one-sub-block box, so the (box, half) of sub-block i is not a function of i alone.
+__device__ __forceinline__ void build_sub_table(const AttnShards& sh, uint32_t* tab, int lane) {
+  int i0 = 0, box0 = 0;
+  for (int s = 0; s < sh.n; ++s) {
+    const int nkv = sh.nkv[s];
+    const int ns = (nkv + 63) >> 6;
+    for (int l = lane; l < ns; l += 32) {
+      const int valid = min(64, nkv - 64 * l);
+      const uint32_t last = ((l & 1) || l == ns - 1) ? 1u : 0u;
+      tab[i0 + l] = uint32_t(box0 + (l >> 1)) | (uint32_t(l & 1) << 20) | (last << 21) | (uint32_t(valid) << 24);
+    }
+    i0 += ns;
+    box0 += (nkv + 127) >> 7;
+  }
+}
+__device__ __forceinline__ int tab_box(uint32_t e) { return int(e & 0xFFFFFu); }
+__device__ __forceinline__ int tab_half(uint32_t e) { return int((e >> 20) & 1u); }
+__device__ __forceinline__ bool tab_last(uint32_t e) { return ((e >> 21) & 1u) != 0; }
+__device__ __forceinline__ int tab_valid(uint32_t e) { return int(e >> 24); }
+
+// TMA producer (one warp, warp-uniform, elect.sync leader): K and V boxes of every shard through kKS-deep mbarrier rings.
+__device__ __forceinline__ void produce_kv(const AttnShards& sh, uint8_t* sK, uint8_t* sV, uint64_t* k_full,
+                                           uint64_t* k_empty, uint64_t* v_full, uint64_t* v_empty, int bh) {
+  const bool leader = elect_one();
+  int g = 0;   // global box counter
+  for (int s = 0; s < sh.n; ++s) {
+    if (sh.ready[s] != nullptr) {
+      // the shard is being written by a peer's copy engine: wait for its arrival flag (written after the copy)
+      if (leader) {
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys_u32(sh.ready[s]) - sh.ready_val[s]) < 0) {
+          if (clock64() - t0 > sh.wait_cycles) {
+            atomicOr(sh.status, 1u);
+            break;
+          }
+          __nanosleep(100);
+        }
+        fence_proxy_async_all();
+      }
+      __syncwarp();
+    }
+    const int nb = (sh.nkv[s] + 127) >> 7;
+    for (int j = 0; j < nb; ++j, ++g) {
+      const int st = g % kKS;
+      const uint32_t ph = (g / kKS) & 1;
+      mbar_wait(&k_empty[st], ph ^ 1);
+      if (leader) {
+        mbar_expect_tx(&k_full[st], kTileBytes);
+        tma_load_3d(sK + st * kTileBytes, &sh.k[s], &k_full[st], 0, j * 128, bh);
+      }
+      mbar_wait(&v_empty[st], ph ^ 1);
+      if (leader) {
+        mbar_expect_tx(&v_full[st], kTileBytes);
+        tma_load_3d(sV + st * kTileBytes, &sh.v[s], &v_full[st], 0, j * 128, bh);
+      }
+    }
+  }
+}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -40,23 +135,31 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// 2^x on the FMA/ALU pipes (Cody-Waite range reduction + degree-3 minimax polynomial, max rel. error 8.8e-5 — far
-// below the bf16 rounding of P): floor via round-down magic add, fraction in [0,1), exponent re-inserted by an
-// integer add.  Offloads part of the softmax exponentials from the 16-op/clk MUFU unit.  x >= 128 yields a NaN
-// bit pattern (exponent field 255), which attn4_kernel's overflow detection catches like MUFU's +inf.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fminf(fmaxf(x, -127.0f), 128.0f);
-  float xr;
-  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(xr) : "f"(x), "f"(12582912.0f));  // 1.5 * 2^23: low mantissa bits = floor(x)
-  const float f = x - (xr - 12582912.0f);
-  float p = fmaf(f, 0.077119089663028717f, 0.227564394474029541f);
-  p = fmaf(p, f, 0.695146143436431885f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+// 2^x for a PAIR on the FMA / ALU pipes (Cody-Waite: floor by a round-down magic add, degree-3 minimax polynomial on
+// the fraction, max rel. error 8.8e-5 — far below the bf16 rounding of P — exponent re-inserted by an integer add).
+// Six packed f32x2 FMA-pipe ops per pair; offloads the 16-op/clk MUFU unit.  x is clamped to [-127, 128]: 2^-127 is a
+// denormal (harmless), x >= 128 yields an exponent field of 255 (inf / NaN), which the overflow detection of the fast
+// path catches exactly like MUFU's +inf.
+__device__ __forceinline__ void ex2_poly_pair(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x0 = fminf(fmaxf(x0, -127.0f), 128.0f);
+  x1 = fminf(fmaxf(x1, -127.0f), 128.0f);
+  const uint64_t xc = pack2(x0, x1);
+  const uint64_t magic = pack2(12582912.0f, 12582912.0f);   // 1.5 * 2^23: low mantissa bits of the sum = floor(x)
+  const uint64_t xr = add2_rm(xc, magic);
+  const uint64_t f = sub2(xc, sub2(xr, magic));              // fraction in [0, 1)
+  uint64_t p = fma2(f, pack2(0.077119089663028717f, 0.077119089663028717f),
+                    pack2(0.227564394474029541f, 0.227564394474029541f));
+  p = fma2(p, f, pack2(0.695146143436431885f, 0.695146143436431885f));
+  p = fma2(p, f, pack2(1.0f, 1.0f));
+  float q0, q1, r0, r1;
+  unpack2(p, q0, q1);
+  unpack2(xr, r0, r1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
 }
 
-// POLY_EVERY = n > 0: every n-th exponential of a row goes to ex2_poly, the others to MUFU.EX2; 0: all MUFU.
-// PROF kernels accumulate per-phase cycle counters (tools/attn_phase_prof.py).
 #define LD_PROF(slot)                                  \
   if constexpr (PROF) {                                \
     const long long now = clock64();                   \
@@ -65,61 +168,46 @@ __device__ __forceinline__ float ex2_poly(float x) {
   }
 
 // ------------------------------------------------------------------------------------------------------------
-// Third-generation kernel: FOUR independent online-softmax streams per CTA, 16 softmax warps (4 per SMSP).
+// Exact path: FOUR independent online-softmax streams per CTA, 16 softmax warps (4 per SMSP).
 //
-// Measured on B200 (tools/softmax_mix_bench.cu): one warp alone runs the exponential mix (FFMA, MUFU.EX2, FADD,
-// F2FP) at ~12 clk/element because its in-order issue cannot overlap MUFU with the dependent ops; two warps per
-// SMSP reach 8.5 and three or more 8.2 — the MUFU limit (8).  So the kernel needs >= 3 warps per SMSP that have
-// exponentials to do at any time.  TMEM (512 columns) cannot hold more than two 128-row query tiles with their
-// accumulators, so each query tile is served by TWO streams that split the keys by 64-key sub-block parity:
-// stream (t, b) owns sub-blocks i = b, b+2, ... of query tile t with its own score buffer S, its own output
-// accumulator O and its own running (max, sum); the two streams of a tile are merged by log-sum-exp in the
-// epilogue.  While one stream waits for the tensor pipe (PV then the next S) the other three keep MUFU busy.
-//   warp 0: TMA producer   warp 1: MMA issuer   (2, 3 idle)   warps 4-19: softmax, stream = (warp-4)/4, TMEM
-//   quadrant = warp%4.  640 threads start at 96 registers; the control warpgroup drops to 48 and the softmax
-//   warpgroups rise to 104 (setmaxnreg.inc only draws on registers released inside the CTA: 6144 >= 4096).
+// Measured on B200 (tools/softmax_mix_bench.cu): one warp alone runs the exponential mix at ~12 clk/element because
+// its in-order issue cannot overlap MUFU with the dependent ops; three or more warps per SMSP reach the MUFU limit.
+// TMEM (512 columns) cannot hold more than two 128-row query tiles with their accumulators, so each query tile is
+// served by TWO streams that split the keys by 64-key sub-block parity: stream (t, b) owns sub-blocks i = b, b+2, ...
+// of query tile t with its own score buffer S, its own output accumulator O and its own running (max, sum); the two
+// streams of a tile are merged by log-sum-exp in the epilogue.
+//   control warps: cw = TMA producer, cw + 1 = MMA issuer; softmax warps sw0 .. sw0 + 15: stream = (warp - sw0) / 4,
+//   TMEM quadrant = warp % 4.  Standalone (variant 1): cw = 0, sw0 = 4; as the in-launch fallback of the fast path:
+//   cw = 16, sw0 = 0 (the register split set up by the fast path — 104 for warps 0-15, 56 for 16-19 — already fits).
 //   TMEM columns: S/P(stream) at 64*stream [0,256) ; O(stream) at 256 + 64*stream [256,512)
-constexpr int kAttn3Threads = 640;
-constexpr int kKS3 = 4;
-constexpr int kAttn3Smem = 2 * kTileBytes + 2 * kKS3 * kTileBytes + 2 * 128 * 2 * 8 /*(m,l) exchange*/ + 1024 + 256;
-
-template <int POLY_EVERY, bool PROF>
-__global__ void __launch_bounds__(kAttn3Threads, 1)
-attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-             const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                // 2 tiles
-  uint8_t* sK = sQ + 2 * kTileBytes;                 // kKS3 tiles
-  uint8_t* sV = sK + kKS3 * kTileBytes;              // kKS3 tiles
-  float2* sML = reinterpret_cast<float2*>(sV + kKS3 * kTileBytes);   // [stream][128] (m * scale_log2, l)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sML + 4 * 128);
+// All 640 threads must call this (it initialises its own barrier set and synchronises the CTA).
+__device__ __forceinline__ void attn_exact_body(const AttnShards& sh, const AttnParams& p, uint8_t* smem,
+                                                uint32_t tmem_base, int cta, int cw, int sw0) {
+  uint8_t* sK = smem + kOffK;
+  uint8_t* sV = smem + kOffV;
+  uint8_t* sQ = smem + kOffQ;
+  const uint32_t* tab = reinterpret_cast<const uint32_t*>(smem + kOffTab);
+  float2* sML = reinterpret_cast<float2*>(smem + kOffML);   // [stream][128] (m * scale_log2, l)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBarsExact);
   uint64_t* q_full = bars;               // 1
-  uint64_t* k_full = bars + 1;           // kKS3
-  uint64_t* k_empty = k_full + kKS3;
-  uint64_t* v_full = k_empty + kKS3;
-  uint64_t* v_empty = v_full + kKS3;
-  uint64_t* s_full = v_empty + kKS3;     // [stream] = 4
+  uint64_t* k_full = bars + 1;           // kKS
+  uint64_t* k_empty = k_full + kKS;
+  uint64_t* v_full = k_empty + kKS;
+  uint64_t* v_empty = v_full + kKS;
+  uint64_t* s_full = v_empty + kKS;      // [stream] = 4
   uint64_t* p_full = s_full + 4;         // [stream] = 4
   uint64_t* o_done = p_full + 4;         // [stream] = 4
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 4);
 
-  // fix-up launch after attn4_kernel: only the CTAs whose fixed reference maximum overflowed are recomputed
-  if (p.redo_only && p.redo[blockIdx.x] == 0) return;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q_blocks = (p.nq + 255) / 256;
-  const int bh = blockIdx.x / q_blocks;
-  const int q0 = (blockIdx.x % q_blocks) * 256;
-  const int n_tiles = (p.nkv + 127) / 128;   // TMA boxes
-  const int n_sub = (p.nkv + 63) / 64;       // 64-key sub-blocks
+  const int bh = cta / q_blocks;
+  const int q0 = (cta % q_blocks) * 256;
+  const int n_sub = sh.n_sub;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_q);
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
+  if (warp == cw && lane == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < kKS3; ++s) {
+    for (int s = 0; s < kKS; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1);
@@ -132,39 +220,20 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
-  // Warps 0 and 1 run warp-uniform code and issue through an elect.sync leader: ptxas then emits back-to-back
-  // UTMALDG / UTCHMMA instead of a per-instruction divergence loop (measured: ~100 clk -> 32 clk per MMA).
-  if (warp < 4) reg_dealloc<48>();
-  if (warp == 0) {
+  if (warp == cw) {
     // ------------------------------------------------------------------ TMA producer
-    const bool leader = elect_one();
-    if (leader) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, 2 * kTileBytes);
-      tma_load_3d(sQ, &tmap_q, q_full, 0, q0, bh);
-      tma_load_3d(sQ + kTileBytes, &tmap_q, q_full, 0, q0 + 128, bh);
+      tma_load_3d(sQ, &sh.q, q_full, 0, q0, bh);
+      tma_load_3d(sQ + kTileBytes, &sh.q, q_full, 0, q0 + 128, bh);
     }
-    int s = 0;
-    uint32_t ph = 0;
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(&k_empty[s], ph ^ 1);
-      if (leader) {
-        mbar_expect_tx(&k_full[s], kTileBytes);
-        tma_load_3d(sK + s * kTileBytes, &tmap_k, &k_full[s], 0, j * 128, bh);
-      }
-      mbar_wait(&v_empty[s], ph ^ 1);
-      if (leader) {
-        mbar_expect_tx(&v_full[s], kTileBytes);
-        tma_load_3d(sV + s * kTileBytes, &tmap_v, &v_full[s], 0, j * 128, bh);
-      }
-      if (++s == kKS3) { s = 0; ph ^= 1; }
-    }
-  } else if (warp == 1) {
+    __syncwarp();
+    produce_kv(sh, sK, sV, k_full, k_empty, v_full, v_empty, bh);
+  } else if (warp == cw + 1) {
     // ------------------------------------------------------------------ MMA issuer
     const bool leader = elect_one();
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 64);
@@ -173,11 +242,10 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK));
     const uint64_t vdesc = make_sdesc_sw128(smem_u32(sV));
     // descriptor address units are 16 B: ring stage = 1024, 64-row half = 512, query tile = 1024
-    // S(t, i) = Q_t K_i^T into the score buffer of stream 2t + (i&1); K sub-block i = rows [64*(i&1), +64) of ring
-    // stage (i>>1) % kKS3
-    auto issue_s = [&](int t, int i) {
+    // S(t, i) = Q_t K_i^T into the score buffer of stream 2t + (i&1)
+    auto issue_s = [&](int t, int i, uint32_t e) {
       const uint64_t adesc = qdesc + uint32_t(t * (kTileBytes >> 4));
-      const uint64_t bdesc = kdesc + uint32_t(((i >> 1) % kKS3) * (kTileBytes >> 4) + (i & 1) * (kTileBytes >> 5));
+      const uint64_t bdesc = kdesc + uint32_t((tab_box(e) % kKS) * (kTileBytes >> 4) + tab_half(e) * (kTileBytes >> 5));
       const int st = 2 * t + (i & 1);
       const uint32_t d = tmem_base + st * 64;
       if (leader) {
@@ -187,8 +255,8 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       }
     };
     // O(stream) += P(t,i) V_i ; P: 128 lanes x 64 keys bf16 = 32 TMEM columns over S(stream)
-    auto issue_pv = [&](int t, int i) {
-      const uint64_t bdesc = vdesc + uint32_t(((i >> 1) % kKS3) * (kTileBytes >> 4) + (i & 1) * (kTileBytes >> 5));
+    auto issue_pv = [&](int t, int i, uint32_t e) {
+      const uint64_t bdesc = vdesc + uint32_t((tab_box(e) % kKS) * (kTileBytes >> 4) + tab_half(e) * (kTileBytes >> 5));
       const int st = 2 * t + (i & 1);
       const uint32_t d = tmem_base + 256 + st * 64;
       const uint32_t a = tmem_base + st * 64;
@@ -200,58 +268,44 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         umma_commit(&o_done[st]);
       }
     };
-    auto k_wait = [&](int tile) { mbar_wait(&k_full[tile % kKS3], (tile / kKS3) & 1); };
-    auto v_wait = [&](int tile) { mbar_wait(&v_full[tile % kKS3], (tile / kKS3) & 1); };
+    auto k_wait = [&](int box) { mbar_wait(&k_full[box % kKS], (box / kKS) & 1); };
+    auto v_wait = [&](int box) { mbar_wait(&v_full[box % kKS], (box / kKS) & 1); };
 
     mbar_wait(q_full, 0);
-    k_wait(0);
-    tc_fence_after();
-    issue_s(0, 0);
-    issue_s(1, 0);
-    if (n_sub > 1) {
-      issue_s(0, 1);
-      issue_s(1, 1);
+    for (int i0 = 0; i0 < 2 && i0 < n_sub; ++i0) {
+      const uint32_t e = tab[i0];
+      if (tab_half(e) == 0) k_wait(tab_box(e));
+      tc_fence_after();
+      issue_s(0, i0, e);
+      issue_s(1, i0, e);
+      if (leader && tab_last(e)) umma_commit(&k_empty[tab_box(e) % kKS]);
     }
-    if (leader) umma_commit(&k_empty[0]);
-    long long w_kv = 0, w_p0 = 0, w_p1 = 0, t_all = 0;
-    if constexpr (PROF) t_all = clock64();
     for (int i = 0; i < n_sub; ++i) {
       const int b = i & 1;
       const uint32_t par = (i >> 1) & 1;
       const bool has_next = (i + 2) < n_sub;
-      long long c0 = 0;
-      if constexpr (PROF) c0 = clock64();
-      if (b == 0) v_wait(i >> 1);
-      if (has_next && b == 0) k_wait((i + 2) >> 1);
-      if constexpr (PROF) { const long long c1 = clock64(); w_kv += c1 - c0; c0 = c1; }
+      const uint32_t e = tab[i];
+      const uint32_t en = has_next ? tab[i + 2] : 0u;
+      if (tab_half(e) == 0) v_wait(tab_box(e));
+      if (has_next && tab_half(en) == 0) k_wait(tab_box(en));
       // tile 0
       mbar_wait(&p_full[0 + b], par);
-      if constexpr (PROF) { const long long c1 = clock64(); w_p0 += c1 - c0; c0 = c1; }
       tc_fence_after();
-      issue_pv(0, i);
-      if (has_next) issue_s(0, i + 2);
+      issue_pv(0, i, e);
+      if (has_next) issue_s(0, i + 2, en);
       // tile 1
-      if constexpr (PROF) c0 = clock64();
       mbar_wait(&p_full[2 + b], par);
-      if constexpr (PROF) w_p1 += clock64() - c0;
       tc_fence_after();
-      issue_pv(1, i);
-      if (leader && (b == 1 || i == n_sub - 1)) umma_commit(&v_empty[(i >> 1) % kKS3]);
+      issue_pv(1, i, e);
+      if (leader && tab_last(e)) umma_commit(&v_empty[tab_box(e) % kKS]);
       if (has_next) {
-        issue_s(1, i + 2);
-        if (leader && (b == 1 || i + 2 == n_sub - 1)) umma_commit(&k_empty[((i + 2) >> 1) % kKS3]);
+        issue_s(1, i + 2, en);
+        if (leader && tab_last(en)) umma_commit(&k_empty[tab_box(en) % kKS]);
       }
     }
-    if constexpr (PROF) {
-      if (leader && p.prof != nullptr) {
-        long long* d = p.prof + ((int64_t)blockIdx.x * 20 + 1) * 8;
-        d[0] = w_kv; d[1] = w_p0; d[2] = w_p1; d[3] = clock64() - t_all;
-      }
-    }
-  } else if (warp >= 4) {
-    reg_alloc<104>();   // 16 warps x 32 x 8 = 4096 <= the 6144 registers released by the control warpgroup
+  } else if (warp >= sw0 && warp < sw0 + 16) {
     // -------------------------------------------------------------------- softmax / correction / epilogue
-    const int st = (warp - 4) >> 2;       // stream
+    const int st = (warp - sw0) >> 2;     // stream
     const int t = st >> 1;                // query tile
     const int b = st & 1;                 // sub-block parity served by this stream
     const int quad = warp & 3;
@@ -264,20 +318,15 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
 
     float m_used = -INFINITY;  // raw-score units
     float l = 0.f;
-    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
-    long long tp = 0;
-    if constexpr (PROF) tp = clock64();
     int kk = 0;   // blocks done by this stream
     for (int i = b; i < n_sub; i += 2, ++kk) {
       mbar_wait(&s_full[st], kk & 1);
       tc_fence_after();
-      LD_PROF(0);
       uint32_t s[64];
       LD_TMEM_LD32(ts + 0, (s + 0));
       LD_TMEM_LD32(ts + 32, (s + 32));
       tmem_ld_wait();
-      LD_PROF(1);
-      const int valid = p.nkv - i * 64;
+      const int valid = tab_valid(tab[i]);
       if (valid < 64) {
 #pragma unroll
         for (int c = 0; c < 64; ++c)
@@ -313,22 +362,13 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         m_used = m_new;
       }
       const float msc = m_used * sl2;
-      LD_PROF(2);
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
       uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         float pv[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int idx = 4 * c + e;
-          const float x = fmaf(__uint_as_float(s[idx]), sl2, -msc);
-          if constexpr (POLY_EVERY > 0) {
-            pv[e] = ((idx % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x) : ex2(x);
-          } else {
-            pv[e] = ex2(x);
-          }
-        }
+        for (int e = 0; e < 4; ++e) pv[e] = ex2(fmaf(__uint_as_float(s[4 * c + e]), sl2, -msc));
         sum0 += pv[0];
         sum1 += pv[1];
         sum2 += pv[2];
@@ -337,12 +377,10 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
         pk[2 * c + 1] = pack_bf16x2(pv[2], pv[3]);
       }
       l += (sum0 + sum1) + (sum2 + sum3);
-      LD_PROF(3);
       LD_TMEM_ST32(ts, pk);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[st]);
-      LD_PROF(4);
     }
 
     // ---- epilogue: merge the two streams of this query tile by log-sum-exp; stream b writes output columns
@@ -350,12 +388,6 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
     if (kk > 0) {
       mbar_wait(&o_done[st], (kk - 1) & 1);
       tc_fence_after();
-    }
-    if constexpr (PROF) {
-      if (lane == 0 && p.prof != nullptr) {
-        long long* d = p.prof + ((int64_t)blockIdx.x * 20 + warp) * 8;
-        for (int e = 0; e < 6; ++e) d[e] = prof_acc[e];
-      }
     }
     sML[st * 128 + row_in_tile] = make_float2(m_used * sl2, l);
     tc_fence_before();
@@ -407,94 +439,99 @@ attn3_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__
       if (b == 0 && p.lse != nullptr) p.lse[(int64_t)bh * p.nq + q_row] = m_all + log2f(l_all);
     }
   }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
-
 // ------------------------------------------------------------------------------------------------------------
-// Fourth-generation kernel: double-buffered 64-key score blocks + 16 softmax warps + Q in TMEM,
-// and NO per-block row maximum.
+// Fast path (round 2, "attn5").
 //
-// Two 128-row query tiles per CTA; each tile has two 64-column score buffers in TMEM so S(t,i+2) is issued right
-// after PV(t,i) and the softmax never waits for the tensor pipe.  Each 32-row TMEM quadrant of a tile is served by
-// a PAIR of warps that split the 64 columns of a sub-block (warp h exponentiates columns [32h, 32h+32)), which
-// puts 4 warps with exponentials on every SMSP (the MUFU unit needs >= 3 to saturate, tools/softmax_mix_bench.cu).
+// Two 128-row query tiles per CTA.  Each 32-row TMEM quadrant of a tile is served by a PAIR of warps that split the 64
+// columns of a sub-block (warp h exponentiates columns [32h, 32h+32)), which puts 4 warps with exponentials on every
+// SMSP.
 //
-// Reference maximum: floating point is scale-invariant, so the online-softmax reference only has to prevent
-// overflow, not track the running maximum.  Each row takes the maximum of its FIRST sub-block as the reference
-// for the whole row (both warps of a pair load that sub-block entirely, so they agree without communicating) and
-// never rescales: later scores may exceed the reference by up to 2^127 before exp2 overflows, and terms far below
-// it flush to zero exactly as their true weight demands.  That removes the 64 FMNMX + vote + correction logic per
-// row and sub-block.  Overflow (a score more than ~127 log2-units above the first block's maximum — never seen on
-// LayerNormed q/k, but constructible) makes the row sum or the output non-finite; the CTA then raises redo[cta],
-// and a second launch of the exact kernel (attn3_kernel, per-block maxima and rescaling) recomputes only the
-// flagged CTAs.  tests/test_kernels_gpu.py::test_attention_overflow_fixup covers that path.
+// What bounds the kernel is the exponential: 16 384 of them per 128x128 score tile at 16 / clk / SM on the MUFU unit
+// is 1024 clk against 512 clk of tensor work.  Round-2 changes, all aimed at that (tools/softmax_mix_bench.cu,
+// profiles/r2_softmax_mix_bench.txt: 8.1 -> 6.0 clk per warp-element with 4 warps per SMSP):
+//   * the row sum is no longer an FADD per element: the tensor core accumulates it, L_t += P(t,i) x ones (an N = 16 MMA
+//     against a constant tile, 12 clk), from exactly the bf16 P values the PV product uses;
+//   * the scale-subtract is a packed FFMA2 per column pair;
+//   * KP of every 16 column pairs are exponentiated by a packed f32x2 polynomial on the FMA pipe (ex2_poly_pair), the
+//     rest by MUFU.EX2;
+//   * the score buffer is handed back to the tensor pipe as soon as the softmax warps have LOADED it (s_free), not when
+//     they have finished with it: S(t,i+1) is computed while the exponentials of S(t,i) run, so one score buffer per tile
+//     suffices and the softmax never waits for the tensor pipe; P has two buffers per tile, so it never waits for PV.
 //
-// Q is stored once into TMEM (bf16 pairs, one row per lane) by the softmax threads, so S = Q K^T runs as a TS-mode
-// MMA whose only shared-memory operand is the K sub-block: 32 clk per 128x64x16 instead of 48 (tools/mma_bench.cu).
-// P has its own 32-column buffer per tile; a warp waits for PV(t,i-1) before overwriting it.
-//   warps 0-15: softmax (tile w>>3, column half (w>>2)&1, TMEM quadrant w&3)   (16 idle)   warp 17: TMA producer
-//   warps 18, 19: MMA issuers of query tile 0 and 1.  One issuer for both tiles spends ~1900 clk per sub-block in
-//   its serial scalar code (barrier polls, descriptor arithmetic, R2UR) and was the bottleneck; the two tiles are
-//   independent instruction streams for the tensor pipe, so each gets its own issuing warp (K/V ring stages are
+// Reference maximum: floating point is scale-invariant, so the online-softmax reference only has to prevent overflow,
+// not track the running maximum.  Each row takes the maximum of its FIRST sub-block as the reference for the whole row
+// (both warps of a pair load that sub-block entirely, so they agree without communicating) and never rescales: later
+// scores may exceed the reference by up to 2^127 before exp2 overflows, and terms far below it flush to zero exactly
+// as their true weight demands.  Overflow (a score more than ~127 log2-units above the first block's maximum — never
+// seen on LayerNormed q/k, but constructible) makes the row sum or the output non-finite; the CTA then re-runs its
+// 256 rows through the exact path above in the same launch.  tests/test_kernels_gpu.py::test_attention_overflow_fixup.
+//
+// Q is stored once into TMEM (bf16 pairs, one row per lane) by the softmax threads, so S = Q K^T runs as a TS-mode MMA
+// whose only shared-memory operand is the K sub-block: 32 clk per 128x64x16 instead of 48 (tools/mma_bench.cu).
+//   warps 0-15: softmax (tile w>>3, column half (w>>2)&1, TMEM quadrant w&3)   16: builds the sub-block table
+//   17: TMA producer   18, 19: MMA issuers of query tile 0 and 1 (independent instruction streams; K/V ring stages are
 //   released by one commit from each).
-//   TMEM columns: S(t,b) at 64(2t+b) [0,256) ; O_t at 256+64t [256,384) ; Q_t at 384+32t [384,448) ;
-//                 P_t at 448+32t [448,512)
-constexpr int kAttn4Threads = 640;
-constexpr int kKS4 = 4;
-constexpr int kAttn4Smem = 2 * kKS4 * kTileBytes + 2 * 2 * 128 * 4 /* row-sum exchange */ + 1024 + 256;
-
-template <int POLY_EVERY, bool PROF, bool PACKED>
-__global__ void __launch_bounds__(kAttn4Threads, 1)
-attn4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
-             const AttnParams p) {
+//   TMEM columns: S_t at 64t [0,128) ; P(t,b) at 128+64t+32b [128,256) ; O_t at 256+64t [256,384) ;
+//                 Q_t at 384+32t [384,448) ; L_t (row sums, 16 identical columns) at 448+16t [448,480)
+template <int KP, bool TRUNC, bool PROF>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;                                // kKS4 tiles
-  uint8_t* sV = sK + kKS4 * kTileBytes;              // kKS4 tiles
-  float* sL = reinterpret_cast<float*>(sV + kKS4 * kTileBytes);   // [tile][half][128] partial row sums
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sL + 2 * 2 * 128);
+  uint8_t* sK = smem + kOffK;
+  uint8_t* sV = smem + kOffV;
+  uint32_t* sOnes = reinterpret_cast<uint32_t*>(smem + kOffOnes);
+  uint32_t* tab = reinterpret_cast<uint32_t*>(smem + kOffTab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBarsFast);
   uint64_t* q_ready = bars;              // [tile] = 2
-  uint64_t* k_full = bars + 2;           // kKS4
-  uint64_t* k_empty = k_full + kKS4;
-  uint64_t* v_full = k_empty + kKS4;
-  uint64_t* v_empty = v_full + kKS4;
-  uint64_t* s_full = v_empty + kKS4;     // [t][b] = 4
-  uint64_t* p_full = s_full + 4;         // [t][b] = 4
-  uint64_t* o_done = p_full + 4;         // [t] = 2
-  uint64_t* all_done = o_done + 2;       // 1: every MMA of this CTA has completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(all_done + 1);
+  uint64_t* k_full = bars + 2;           // kKS
+  uint64_t* k_empty = k_full + kKS;
+  uint64_t* v_full = k_empty + kKS;
+  uint64_t* v_empty = v_full + kKS;
+  uint64_t* s_full = v_empty + kKS;      // [t] = 2   S(t,i) is in TMEM
+  uint64_t* s_free = s_full + 2;         // [t] = 2   the 8 softmax warps of tile t hold S(t,i) in registers
+  uint64_t* p_full = s_free + 2;         // [t][b] = 4  P(t,i) is in TMEM
+  uint64_t* p_free = p_full + 4;         // [t][b] = 4  PV(t,i) has consumed P buffer b
+  uint64_t* all_done = p_free + 4;       // 1: every MMA of this CTA has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffSlot);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q_blocks = (p.nq + 255) / 256;
   const int bh = blockIdx.x / q_blocks;
   const int q0 = (blockIdx.x % q_blocks) * 256;
-  const int n_tiles = (p.nkv + 127) / 128;   // TMA boxes
-  const int n_sub = (p.nkv + 63) / 64;       // 64-key sub-blocks
+  const int n_sub = sh.n_sub;
 
   if (warp == 17 && lane == 0) {
-    tma_prefetch_desc(&tmap_k);
-    tma_prefetch_desc(&tmap_v);
-    for (int s = 0; s < kKS4; ++s) {
+    tma_prefetch_desc(&sh.q);
+    for (int s = 0; s < sh.n; ++s) {
+      tma_prefetch_desc(&sh.k[s]);
+      tma_prefetch_desc(&sh.v[s]);
+    }
+    for (int s = 0; s < kKS; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], 2);
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 2);
     }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 256);
-    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_ready[i], 128);
-      mbar_init(&o_done[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 8);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&p_full[i], 8);
+      mbar_init(&p_free[i], 1);
     }
     mbar_init(all_done, 2);
     fence_barrier_init();
+  }
+  if (warp == 16) {
+    build_sub_table(sh, tab, lane);
+    for (int i = lane; i < 512; i += 32) sOnes[i] = 0x3F803F80u;   // bf16 1.0 pairs
+    fence_proxy_async_smem();   // the ones tile is read by the async proxy (tcgen05.mma B operand)
   }
   if (warp == 19) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
@@ -506,294 +543,260 @@ attn4_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__
   // The producer and issuer warps run warp-uniform code and issue through an elect.sync leader: ptxas then emits
   // back-to-back UTMALDG / UTCHMMA instead of a per-instruction divergence loop (measured: ~100 clk -> 32 clk).
   if (warp >= 16) reg_dealloc<56>();   // releases 4 x 32 x 40 = 5120 registers
-  if (warp == 17) {
-    // ------------------------------------------------------------------ TMA producer
-    const bool leader = elect_one();
-    int s = 0;
-    uint32_t ph = 0;
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(&k_empty[s], ph ^ 1);
-      if (leader) {
-        mbar_expect_tx(&k_full[s], kTileBytes);
-        tma_load_3d(sK + s * kTileBytes, &tmap_k, &k_full[s], 0, j * 128, bh);
-      }
-      mbar_wait(&v_empty[s], ph ^ 1);
-      if (leader) {
-        mbar_expect_tx(&v_full[s], kTileBytes);
-        tma_load_3d(sV + s * kTileBytes, &tmap_v, &v_full[s], 0, j * 128, bh);
-      }
-      if (++s == kKS4) { s = 0; ph ^= 1; }
-    }
-  } else if (warp >= 18) {
-    // ------------------------------------------------------------------ MMA issuer of query tile t
-    const int t = warp - 18;
-    const bool leader = elect_one();
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64);
-    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);  // B (=V) is N-major
-    const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK));
-    const uint64_t vdesc = make_sdesc_sw128(smem_u32(sV));
-    const uint32_t tm_s = tmem_base + 128 * t;        // S(t,0); S(t,1) 64 columns further
-    const uint32_t tm_o = tmem_base + 256 + 64 * t;
-    const uint32_t tm_q = tmem_base + 384 + 32 * t;
-    const uint32_t tm_p = tmem_base + 448 + 32 * t;
-    // descriptor address units are 16 B: ring stage = 1024, 64-row half = 512
-    // S(t, i) = Q_t K_i^T into buffer i&1; Q_t from TMEM (8 columns per 16-dim K step)
-    auto issue_s = [&](int i) {
-      const uint64_t bdesc = kdesc + uint32_t(((i >> 1) % kKS4) * (kTileBytes >> 4) + (i & 1) * (kTileBytes >> 5));
-      const uint32_t d = tm_s + (i & 1) * 64;
-      if (leader) {
+  if (!p.exact_only) {
+    if (warp == 17) {
+      produce_kv(sh, sK, sV, k_full, k_empty, v_full, v_empty, bh);
+    } else if (warp >= 18) {
+      // ------------------------------------------------------------------ MMA issuer of query tile t
+      const int t = warp - 18;
+      const bool leader = elect_one();
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);  // B (=V) is N-major
+      constexpr uint32_t idesc_l = make_idesc_bf16(128, 16);               // row sums: P x ones[64 keys x 16]
+      const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK));
+      const uint64_t vdesc = make_sdesc_sw128(smem_u32(sV));
+      const uint64_t odesc = make_sdesc_sw128(smem_u32(sOnes));
+      const uint32_t tm_s = tmem_base + 64 * t;
+      const uint32_t tm_p = tmem_base + 128 + 64 * t;   // P(t,0); P(t,1) 32 columns further
+      const uint32_t tm_o = tmem_base + 256 + 64 * t;
+      const uint32_t tm_q = tmem_base + 384 + 32 * t;
+      const uint32_t tm_l = tmem_base + 448 + 16 * t;
+      long long w_k = 0, w_v = 0, w_p = 0, w_s = 0, i_s = 0, i_pv = 0, t_all = 0;
+      // descriptor address units are 16 B: ring stage = 1024, 64-row half = 512
+      // S(t, i) = Q_t K_i^T ; Q_t from TMEM (8 columns per 16-dim K step)
+      auto s_step = [&](int i) {
+        const uint32_t e = tab[i];
+        const int st = tab_box(e) % kKS;
+        long long c0 = 0;
+        if constexpr (PROF) c0 = clock64();
+        if (tab_half(e) == 0) mbar_wait(&k_full[st], (tab_box(e) / kKS) & 1);
+        if constexpr (PROF) { const long long c1 = clock64(); w_k += c1 - c0; c0 = c1; }
+        tc_fence_after();
+        const uint64_t bdesc = kdesc + uint32_t(st * (kTileBytes >> 4) + tab_half(e) * (kTileBytes >> 5));
+        if (leader) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ts(d, tm_q + 8 * k, bdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[2 * t + (i & 1)]);
-      }
-    };
-    // O_t += P(t,i) V_i ; P: 128 lanes x 64 keys bf16 = the tile's 32-column P buffer
-    auto issue_pv = [&](int i) {
-      const uint64_t bdesc = vdesc + uint32_t(((i >> 1) % kKS4) * (kTileBytes >> 4) + (i & 1) * (kTileBytes >> 5));
-      if (leader) {
-        // 16 keys per step: 16 rows x 128 B = 2048 B (encoded 128)
-        umma_ts(tm_o, tm_p, bdesc, idesc_o, i != 0);
-#pragma unroll
-        for (int k = 1; k < 4; ++k) umma_ts(tm_o, tm_p + k * 8, bdesc + 128 * k, idesc_o, 1u);
-        umma_commit(&o_done[t]);
-      }
-    };
-    auto k_wait = [&](int tile) { mbar_wait(&k_full[tile % kKS4], (tile / kKS4) & 1); };
-    auto v_wait = [&](int tile) { mbar_wait(&v_full[tile % kKS4], (tile / kKS4) & 1); };
-
-    mbar_wait(&q_ready[t], 0);
-    k_wait(0);
-    tc_fence_after();
-    issue_s(0);
-    if (n_sub > 1) issue_s(1);
-    if (leader) umma_commit(&k_empty[0]);
-    long long w_kv = 0, w_p0 = 0, t_all = 0, w_ipv = 0, w_is = 0;
-    if constexpr (PROF) t_all = clock64();
-    for (int i = 0; i < n_sub; ++i) {
-      const int b = i & 1;
-      const bool has_next = (i + 2) < n_sub;
-      long long c0 = 0;
-      if constexpr (PROF) c0 = clock64();
-      if (b == 0) v_wait(i >> 1);
-      if (has_next && b == 0) k_wait((i + 2) >> 1);
-      if constexpr (PROF) { const long long c1 = clock64(); w_kv += c1 - c0; c0 = c1; }
-      mbar_wait(&p_full[2 * t + b], (i >> 1) & 1);
-      if constexpr (PROF) { const long long c1 = clock64(); w_p0 += c1 - c0; c0 = c1; }
-      tc_fence_after();
-      issue_pv(i);
-      if constexpr (PROF) { const long long c1 = clock64(); w_ipv += c1 - c0; c0 = c1; }
-      if (leader && (b == 1 || i == n_sub - 1)) umma_commit(&v_empty[(i >> 1) % kKS4]);
-      if (has_next) {
-        issue_s(i + 2);
-        if (leader && (b == 1 || i + 2 == n_sub - 1)) umma_commit(&k_empty[((i + 2) >> 1) % kKS4]);
-      }
-      if constexpr (PROF) w_is += clock64() - c0;
-    }
-    if (leader) umma_commit(all_done);
-    if constexpr (PROF) {
-      if (leader && p.prof != nullptr) {
-        long long* d = p.prof + ((int64_t)blockIdx.x * 20 + warp) * 8;
-        d[0] = w_kv; d[1] = w_p0; d[2] = 0; d[3] = clock64() - t_all; d[4] = w_ipv; d[5] = w_is;
-      }
-    }
-  } else if (warp < 16) {
-    reg_alloc<104>();   // 16 warps x 32 x 8 = 4096 <= the 5120 registers released by the control warpgroup
-    // -------------------------------------------------------------------- softmax / correction / epilogue
-    const int t = warp >> 3;                    // query tile
-    const int h = (warp >> 2) & 1;              // column half of every sub-block exponentiated by this warp
-    const int quad = warp & 3;
-    const int row_in_tile = quad * 32 + lane;
-    const int q_row = q0 + t * 128 + row_in_tile;
-    const uint32_t lane_base = uint32_t(quad * 32) << 16;
-    const uint32_t ts = tmem_base + lane_base + t * 128;         // S(t,0); S(t,1) is 64 columns further
-    const uint32_t to = tmem_base + lane_base + 256 + t * 64;    // O_t
-    const float sl2 = p.scale_log2;
-
-    if (h == 0) {
-      // Q row -> TMEM (bf16 pairs: column c holds dims 2c, 2c+1), zero beyond nq
-      uint32_t qr[32];
-      if (q_row < p.nq) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.q + ((int64_t)bh * p.q_rows + q_row) * 64);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 v = __ldg(src + c);
-          qr[4 * c] = v.x; qr[4 * c + 1] = v.y; qr[4 * c + 2] = v.z; qr[4 * c + 3] = v.w;
+          for (int k = 0; k < 4; ++k) umma_ts(tm_s, tm_q + 8 * k, bdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[t]);
+          if (tab_last(e)) umma_commit(&k_empty[st]);
         }
-      } else {
+        if constexpr (PROF) { __syncwarp(); i_s += clock64() - c0; }
+      };
+      // O_t += P(t,i) V_i and L_t += P(t,i) 1 ; P: 128 lanes x 64 keys bf16 = 32 columns; 16 keys (8 columns) per MMA
+      auto pv_step = [&](int i) {
+        const uint32_t e = tab[i];
+        const int st = tab_box(e) % kKS;
+        const int b = i & 1;
+        long long c0 = 0;
+        if constexpr (PROF) c0 = clock64();
+        if (tab_half(e) == 0) mbar_wait(&v_full[st], (tab_box(e) / kKS) & 1);
+        if constexpr (PROF) { const long long c1 = clock64(); w_v += c1 - c0; c0 = c1; }
+        mbar_wait(&p_full[2 * t + b], (i >> 1) & 1);
+        if constexpr (PROF) { const long long c1 = clock64(); w_p += c1 - c0; c0 = c1; }
+        tc_fence_after();
+        const uint64_t bdesc = vdesc + uint32_t(st * (kTileBytes >> 4) + tab_half(e) * (kTileBytes >> 5));
+        const uint32_t a = tm_p + 32 * b;
+        if (leader) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) qr[c] = 0u;
-      }
-      LD_TMEM_ST32(tmem_base + lane_base + 384 + 32 * t, qr);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&q_ready[t]);
-    }
-
-    float msc = 0.f;   // reference maximum of the row (first sub-block) * scale_log2
-    float l = 0.f;
-    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
-    long long tp = 0;
-    if constexpr (PROF) tp = clock64();
-    const uint32_t tp_addr = tmem_base + lane_base + 448 + 32 * t + 16 * h;
-    bool s_ready = false;   // s_full(i) already observed complete by the probe of the previous iteration
-    for (int i = 0; i < n_sub; ++i) {
-      const int b = i & 1;
-      const uint32_t tsb = ts + b * 64;
-      if (!s_ready) mbar_wait(&s_full[2 * t + b], (i >> 1) & 1);
-      tc_fence_after();
-      LD_PROF(0);
-      uint32_t s[32];   // this warp's column half
-      LD_TMEM_LD32(tsb + 32 * h, s);
-      const int valid = p.nkv - i * 64 - 32 * h;
-      if (i == 0) {
-        // reference maximum of the row = maximum of the whole first sub-block (identical in both warps of the pair)
-        uint32_t so[32];
-        LD_TMEM_LD32(tsb + 32 * (h ^ 1), so);
-        tmem_ld_wait();
-        const int valid_o = p.nkv - 32 * (h ^ 1);
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          if (c < valid) mx = fmaxf(mx, __uint_as_float(s[c]));
-          if (c < valid_o) mx = fmaxf(mx, __uint_as_float(so[c]));
-        }
-        msc = mx * sl2;
-      } else {
-        tmem_ld_wait();
-      }
-      LD_PROF(1);
-      if (valid < 32) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c >= valid) s[c] = 0xff800000u;  // -inf
-      }
-      LD_PROF(2);
-      // Probe the two barriers the end of this iteration and the start of the next one depend on now, so their
-      // ~100-clk round trips overlap the exponentials (both are almost always complete already).
-      const bool pv_done = (i == 0) || mbar_test_wait(&o_done[t], (i - 1) & 1);
-      s_ready = (i + 1 < n_sub) && mbar_test_wait(&s_full[2 * t + (b ^ 1)], ((i + 1) >> 1) & 1);
-      uint32_t pk[16];
-      if constexpr (PACKED) {
-        // packed f32x2 FMA / ADD: same FMA-pipe throughput but half the issue slots for the scale-subtract and the row
-        // sums, which is what makes the polynomial split pay (tools/softmax_mix_bench.cu: 6.5 clk/element with every
-        // 4th exponential on the FMA pipe at 4 warps per SMSP, against 8.2 for the plain mix)
-        uint64_t sc2, nm2, sum01 = 0, sum23 = 0;
-        asm("mov.b64 %0, {%1, %1};" : "=l"(sc2) : "f"(sl2));
-        asm("mov.b64 %0, {%1, %1};" : "=l"(nm2) : "f"(-msc));
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          uint64_t a01, a23;
-          asm("mov.b64 %0, {%1, %2};" : "=l"(a01) : "r"(s[4 * c]), "r"(s[4 * c + 1]));
-          asm("mov.b64 %0, {%1, %2};" : "=l"(a23) : "r"(s[4 * c + 2]), "r"(s[4 * c + 3]));
-          asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a01) : "l"(sc2), "l"(nm2));
-          asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a23) : "l"(sc2), "l"(nm2));
-          float x[4], pv[4];
-          asm("mov.b64 {%0, %1}, %2;" : "=f"(x[0]), "=f"(x[1]) : "l"(a01));
-          asm("mov.b64 {%0, %1}, %2;" : "=f"(x[2]), "=f"(x[3]) : "l"(a23));
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int idx = 4 * c + e;
-            if constexpr (POLY_EVERY > 0) {
-              pv[e] = ((idx % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x[e]) : ex2(x[e]);
-            } else {
-              pv[e] = ex2(x[e]);
-            }
+          for (int k = 0; k < 4; ++k) {
+            // 16 keys per step: 16 rows x 128 B = 2048 B (encoded 128)
+            umma_ts(tm_o, a + 8 * k, bdesc + 128 * k, idesc_o, (i | k) != 0);
+            umma_ts(tm_l, a + 8 * k, odesc, idesc_l, (i | k) != 0);
           }
-          uint64_t p01, p23;
-          asm("mov.b64 %0, {%1, %2};" : "=l"(p01) : "f"(pv[0]), "f"(pv[1]));
-          asm("mov.b64 %0, {%1, %2};" : "=l"(p23) : "f"(pv[2]), "f"(pv[3]));
-          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sum01) : "l"(p01));
-          asm("add.rn.f32x2 %0, %0, %1;" : "+l"(sum23) : "l"(p23));
-          pk[2 * c] = pack_bf16x2(pv[0], pv[1]);
-          pk[2 * c + 1] = pack_bf16x2(pv[2], pv[3]);
+          umma_commit(&p_free[2 * t + b]);
+          if (tab_last(e)) umma_commit(&v_empty[st]);
         }
-        float s0, s1, s2, s3;
-        asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(sum01));
-        asm("mov.b64 {%0, %1}, %2;" : "=f"(s2), "=f"(s3) : "l"(sum23));
-        l += (s0 + s1) + (s2 + s3);
-      } else {
-        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float pv[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int idx = 4 * c + e;
-            const float x = fmaf(__uint_as_float(s[idx]), sl2, -msc);
-            if constexpr (POLY_EVERY > 0) {
-              pv[e] = ((idx % POLY_EVERY) == POLY_EVERY - 1) ? ex2_poly(x) : ex2(x);
-            } else {
-              pv[e] = ex2(x);
-            }
-          }
-          sum0 += pv[0];
-          sum1 += pv[1];
-          sum2 += pv[2];
-          sum3 += pv[3];
-          pk[2 * c] = pack_bf16x2(pv[0], pv[1]);
-          pk[2 * c + 1] = pack_bf16x2(pv[2], pv[3]);
+        if constexpr (PROF) { __syncwarp(); i_pv += clock64() - c0; }
+      };
+      mbar_wait(&q_ready[t], 0);
+      if constexpr (PROF) t_all = clock64();
+      s_step(0);
+      for (int i = 0; i < n_sub; ++i) {
+        if (i + 1 < n_sub) {
+          long long c0 = 0;
+          if constexpr (PROF) c0 = clock64();
+          mbar_wait(&s_free[t], i & 1);      // the softmax warps hold S(t,i) in registers: the buffer may be rewritten
+          if constexpr (PROF) w_s += clock64() - c0;
+          s_step(i + 1);
         }
-        l += (sum0 + sum1) + (sum2 + sum3);
+        pv_step(i);
       }
-      LD_PROF(3);
-      if (!pv_done) mbar_wait(&o_done[t], (i - 1) & 1);   // PV(t,i-1) has consumed the P buffer
-      LD_TMEM_ST16(tp_addr, pk);
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_full[2 * t + b]);
-      LD_PROF(4);
-    }
+      if (leader) umma_commit(all_done);
+      if constexpr (PROF) {
+        if (leader && p.prof != nullptr) {
+          long long* d = p.prof + ((int64_t)blockIdx.x * 20 + warp) * 8;
+          d[0] = w_k; d[1] = w_v; d[2] = w_p; d[3] = w_s; d[4] = i_s; d[5] = i_pv; d[6] = clock64() - t_all;
+        }
+      }
+    } else if (warp < 16) {
+      reg_alloc<104>();   // 16 warps x 32 x 8 = 4096 <= the 5120 registers released by the control warpgroup
+      // -------------------------------------------------------------------- softmax / epilogue
+      const int t = warp >> 3;                    // query tile
+      const int h = (warp >> 2) & 1;              // column half of every sub-block exponentiated by this warp
+      const int quad = warp & 3;
+      const int row_in_tile = quad * 32 + lane;
+      const int q_row = q0 + t * 128 + row_in_tile;
+      const uint32_t lane_base = uint32_t(quad * 32) << 16;
+      const uint32_t ts = tmem_base + lane_base + t * 64;                   // S_t
+      const uint32_t tpp = tmem_base + lane_base + 128 + t * 64 + 16 * h;   // this warp's 16 columns of P(t,0)
+      const uint32_t to = tmem_base + lane_base + 256 + t * 64;             // O_t
+      const float sl2 = p.scale_log2;
 
-    // ---- epilogue: total row sum = the two halves' partial sums (same reference maximum); warp h writes output
-    //      columns [32h, 32h+32) of the head.  The softmax may run up to two PVs ahead of the tensor pipe, so a
-    //      parity wait on o_done could alias here (both last phases may already have completed): the end of all
-    //      MMAs has its own single-use barrier.
-    mbar_wait(all_done, 0);
-    tc_fence_after();
-    if constexpr (PROF) {
-      if (lane == 0 && p.prof != nullptr) {
-        long long* d = p.prof + ((int64_t)blockIdx.x * 20 + warp) * 8;
-        for (int e = 0; e < 6; ++e) d[e] = prof_acc[e];
+      if (h == 0) {
+        // Q row -> TMEM (bf16 pairs: column c holds dims 2c, 2c+1), zero beyond nq
+        uint32_t qr[32];
+        if (q_row < p.nq) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.q + ((int64_t)bh * p.q_rows + q_row) * 64);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 v = __ldg(src + c);
+            qr[4 * c] = v.x; qr[4 * c + 1] = v.y; qr[4 * c + 2] = v.z; qr[4 * c + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) qr[c] = 0u;
+        }
+        LD_TMEM_ST32(tmem_base + lane_base + 384 + 32 * t, qr);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&q_ready[t]);
+      }
+
+      float msc = 0.f;   // reference maximum of the row (first sub-block) * scale_log2
+      long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+      long long tp = 0;
+      if constexpr (PROF) tp = clock64();
+      bool s_ready = false;   // s_full(i) already observed complete by the probe of the previous iteration
+      for (int i = 0; i < n_sub; ++i) {
+        const int b = i & 1;
+        if (!s_ready) mbar_wait(&s_full[t], i & 1);
+        tc_fence_after();
+        LD_PROF(0);
+        uint32_t s[32];   // this warp's column half
+        LD_TMEM_LD32(ts + 32 * h, s);
+        const int valid = tab_valid(tab[i]) - 32 * h;
+        if (i == 0) {
+          // reference maximum of the row = maximum of the whole first sub-block (identical in both warps of the pair)
+          uint32_t so[32];
+          LD_TMEM_LD32(ts + 32 * (h ^ 1), so);
+          tmem_ld_wait();
+          const int valid_o = tab_valid(tab[0]) - 32 * (h ^ 1);
+          float mx = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (c < valid) mx = fmaxf(mx, __uint_as_float(s[c]));
+            if (c < valid_o) mx = fmaxf(mx, __uint_as_float(so[c]));
+          }
+          msc = mx * sl2;
+        } else {
+          tmem_ld_wait();
+        }
+        // S(t,i) is in registers: hand the score buffer back to the tensor pipe (S(t,i+1) runs under the exponentials)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);
+        LD_PROF(1);
+        if (valid < 32) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c >= valid) s[c] = 0xff800000u;  // -inf
+        }
+        LD_PROF(2);
+        uint32_t pk[16];
+        const uint64_t sc2 = pack2(sl2, sl2), nm2 = pack2(-msc, -msc);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const uint64_t x2 = fma2(pack2u(s[2 * c], s[2 * c + 1]), sc2, nm2);
+          float p0, p1;
+          if (KP > 0 && ((c * KP) % 16) < KP) {   // KP of 16 pairs, evenly spread, on the FMA pipe
+            ex2_poly_pair(x2, p0, p1);
+          } else {
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            p0 = ex2(x0);
+            p1 = ex2(x1);
+          }
+          if constexpr (TRUNC) {
+            // bf16 by truncation (one byte permute instead of the half-rate F2FP): the bias cancels because the row
+            // sum is accumulated from the same truncated values
+            asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(pk[c]) : "r"(__float_as_uint(p0)), "r"(__float_as_uint(p1)));
+          } else {
+            pk[c] = pack_bf16x2(p0, p1);
+          }
+        }
+        LD_PROF(3);
+        // probe the barrier the next iteration starts with (almost always complete: S(t,i+1) was issued at s_free(i))
+        s_ready = (i + 1 < n_sub) && mbar_test_wait(&s_full[t], (i + 1) & 1);
+        if (i >= 2) {
+          mbar_wait(&p_free[2 * t + b], ((i >> 1) - 1) & 1);   // PV(t,i-2) has consumed this P buffer (long ago)
+          tc_fence_after();
+        }
+        LD_TMEM_ST16(tpp + 32 * b, pk);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[2 * t + b]);
+        LD_PROF(4);
+      }
+
+      // ---- epilogue: the row sum comes from the tensor core (L_t); warp h writes output columns [32h, 32h+32)
+      mbar_wait(all_done, 0);
+      tc_fence_after();
+      if constexpr (PROF) {
+        if (lane == 0 && p.prof != nullptr) {
+          long long* d = p.prof + ((int64_t)blockIdx.x * 20 + warp) * 8;
+          for (int e = 0; e < 6; ++e) d[e] = prof_acc[e];
+        }
+      }
+      uint32_t lbits;
+      LD_TMEM_LD1(tmem_base + lane_base + 448 + 16 * t, lbits);
+      const int c0 = 32 * h;
+      uint32_t o[32];
+      LD_TMEM_LD32(to + c0, o);
+      tmem_ld_wait();
+      const float l_all = __uint_as_float(lbits);
+      const float inv_l = 1.0f / l_all;
+      const bool valid_row = q_row < p.nq;
+      const int bb = bh / p.heads, hd = bh - bb * p.heads;
+      if (valid_row) {
+        bad = !(l_all < INFINITY) || !(l_all > 0.f);   // inf / NaN row sum (or everything flushed to zero)
+        bf16* orow = p.out + ((int64_t)bb * p.nq + q_row) * (p.heads * 64) + hd * 64 + c0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            f[e] = __uint_as_float(o[g * 8 + e]) * inv_l;
+            bad |= !(fabsf(f[e]) < INFINITY);
+          }
+          uint4 v;
+          v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+          v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(orow + g * 8) = v;
+          if (p.out_f32 != nullptr) {
+            float* of = p.out_f32 + ((int64_t)bh * p.nq + q_row) * 64 + c0 + g * 8;
+            *reinterpret_cast<float4*>(of) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(of + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          }
+        }
+        // truncated P values are low by 2^-9 on average (uniform mantissa tails): the normalisation above uses the same
+        // values and needs no correction, the exported log-sum-exp does
+        if (h == 0 && p.lse != nullptr)
+          p.lse[(int64_t)bh * p.nq + q_row] = msc + log2f(TRUNC ? l_all * 1.001953125f : l_all);
       }
     }
-    sL[(t * 2 + h) * 128 + row_in_tile] = l;
-    named_bar_sync(1 + t, 256);     // the 8 warps of query tile t
-    const float l_all = l + sL[(t * 2 + (h ^ 1)) * 128 + row_in_tile];
-    const float inv_l = 1.0f / l_all;
-    const bool valid_row = q_row < p.nq;
-    const int bb = bh / p.heads, hd = bh - bb * p.heads;
-    const int c0 = 32 * h;
-    uint32_t o[32];
-    LD_TMEM_LD32(to + c0, o);
-    tmem_ld_wait();
-    if (valid_row) {
-      bad = !(l_all < INFINITY) || !(l_all > 0.f);   // inf / NaN row sum (or everything flushed to zero)
-      bf16* orow = p.out + ((int64_t)bb * p.nq + q_row) * (p.heads * 64) + hd * 64 + c0;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          f[e] = __uint_as_float(o[g * 8 + e]) * inv_l;
-          bad |= !(fabsf(f[e]) < INFINITY);
-        }
-        uint4 v;
-        v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
-        v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(orow + g * 8) = v;
-        if (p.out_f32 != nullptr) {
-          float* of = p.out_f32 + ((int64_t)bh * p.nq + q_row) * 64 + c0 + g * 8;
-          *reinterpret_cast<float4*>(of) = make_float4(f[0], f[1], f[2], f[3]);
-          *reinterpret_cast<float4*>(of + 4) = make_float4(f[4], f[5], f[6], f[7]);
-        }
-      }
-      if (h == 0 && p.lse != nullptr) p.lse[(int64_t)bh * p.nq + q_row] = msc + log2f(l_all);
-    }
+  } else {
+    if (warp < 16) reg_alloc<104>();
   }
 
   tc_fence_before();
-  const int any_bad = __syncthreads_or(bad ? 1 : 0);
-  if (threadIdx.x == 0) p.redo[blockIdx.x] = any_bad;   // 1: the exact kernel recomputes this CTA's 256 rows
+  const int redo = __syncthreads_or((bad || p.exact_only) ? 1 : 0);
+  if (redo) {
+    // the fixed reference maximum overflowed somewhere in this CTA's 256 rows (or variant 1): exact path, same launch
+    tc_fence_after();
+    attn_exact_body(sh, p, smem, tmem_base, blockIdx.x, /*cw=*/16, /*sw0=*/0);
+    tc_fence_before();
+    __syncthreads();
+  }
   if (warp == 19) tmem_dealloc<512>(tmem_base);
 }
 
@@ -830,30 +833,19 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(float* __restrict__ o_a
   if ((gid & 15) == 0) lse_acc[row] = m + log2f(wa + wb);
 }
 
-template <int POLY_EVERY, bool PROF = false>
-static int launch_attn3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& prm,
-                        int grid, cudaStream_t st) {
-  auto kern = attn3_kernel<POLY_EVERY, PROF>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3Smem));
-    attr_set = true;
+template <int KP, bool TRUNC, bool PROF = false>
+static int launch_attn5(const AttnShards& sh, const AttnParams& prm, int grid, cudaStream_t st) {
+  auto kern = attn5_kernel<KP, TRUNC, PROF>;
+  // per template instantiation and device (cudaFuncSetAttribute is per device)
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  LD_CHECK_CUDA(cudaGetDevice(&dev));
+  LD_CHECK_ARG(dev >= 0 && dev < 64, "ld_attention: device index out of range");
+  if (!attr_set[dev]) {
+    LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    attr_set[dev] = true;
   }
-  kern<<<grid, kAttn3Threads, kAttn3Smem, st>>>(tq, tk, tv, prm);
-  LD_CHECK_CUDA(cudaGetLastError());
-  return LD_OK;
-}
-
-template <int POLY_EVERY, bool PROF = false, bool PACKED = false>
-static int launch_attn4(const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& prm, int grid,
-                        cudaStream_t st) {
-  auto kern = attn4_kernel<POLY_EVERY, PROF, PACKED>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn4Smem));
-    attr_set = true;
-  }
-  kern<<<grid, kAttn4Threads, kAttn4Smem, st>>>(tk, tv, prm);
+  kern<<<grid, kAttnThreads, kAttnSmem, st>>>(sh, prm);
   LD_CHECK_CUDA(cudaGetLastError());
   return LD_OK;
 }
@@ -862,115 +854,133 @@ static int launch_attn4(const CUtensorMap& tk, const CUtensorMap& tv, const Attn
 
 using namespace ld;
 
-// redo flags of the attn4 + fix-up pair: one int per CTA, per device, grown on demand (allocation only on first use
-// or growth, so a warmed-up step allocates nothing)
-static int* g_redo[64] = {nullptr};
-static int g_redo_cap[64] = {0};
-static int redo_buffer(int grid, int** out) {
+static long long* g_attn_prof = nullptr;
+// Debug hook (tools/attn_phase_prof.py): per-(CTA, warp) phase cycle counters for the next attention calls.
+extern "C" void ld_debug_attn_prof(long long* buf) { g_attn_prof = buf; }
+
+// per-device status word of the shard waits (bit 0: a wait timed out), allocated on first use
+static uint32_t* g_status[64] = {nullptr};
+static int status_word(uint32_t** out) {
   int dev = 0;
   LD_CHECK_CUDA(cudaGetDevice(&dev));
-  LD_CHECK_ARG(dev >= 0 && dev < 64, "ld_attention_bf16: device index out of range");
-  if (grid > g_redo_cap[dev]) {
-    if (g_redo[dev] != nullptr) LD_CHECK_CUDA(cudaFree(g_redo[dev]));
-    g_redo[dev] = nullptr;
-    g_redo_cap[dev] = 0;
-    const int cap = grid + grid / 2 + 1024;
-    LD_CHECK_CUDA(cudaMalloc(&g_redo[dev], sizeof(int) * (size_t)cap));
-    g_redo_cap[dev] = cap;
+  LD_CHECK_ARG(dev >= 0 && dev < 64, "ld_attention: device index out of range");
+  if (g_status[dev] == nullptr) {
+    LD_CHECK_CUDA(cudaMalloc(&g_status[dev], 256));
+    LD_CHECK_CUDA(cudaMemset(g_status[dev], 0, 256));
   }
-  *out = g_redo[dev];
+  *out = g_status[dev];
   return LD_OK;
 }
 
-static long long* g_attn_prof = nullptr;
-// Debug hook (tools/attn_phase_prof.py): per-(CTA, warp) phase cycle counters for the next ld_attention_bf16 calls.
-extern "C" void ld_debug_attn_prof(long long* buf) { g_attn_prof = buf; }
+extern "C" int ld_attention_status(unsigned int* host_out, int reset) {
+  uint32_t* w = nullptr;
+  int rc = status_word(&w);
+  if (rc != LD_OK) return rc;
+  LD_CHECK_ARG(host_out != nullptr, "ld_attention_status: null pointer");
+  LD_CHECK_CUDA(cudaMemcpy(host_out, w, 4, cudaMemcpyDeviceToHost));
+  if (reset) LD_CHECK_CUDA(cudaMemset(w, 0, 4));
+  return LD_OK;
+}
 
-extern "C" int ld_attention_bf16(const void* q, const void* k, const void* v, void* out, float* lse, float* out_f32,
-                                 int batch, int heads, int nq, int q_rows, int nkv, int kv_rows, int variant,
-                                 void* stream) {
+extern "C" int ld_attention_shards_bf16(const void* q, const ld_kv_shard* shards, int n_shards, void* out, float* lse,
+                                        float* out_f32, int batch, int heads, int nq, int q_rows, int variant,
+                                        void* stream) {
   int rc = check_device();
   if (rc != LD_OK) return rc;
-  LD_CHECK_ARG(q && k && v && out, "ld_attention_bf16: null pointer");
-  LD_CHECK_ARG(batch > 0 && heads > 0 && nq > 0 && nkv > 0, "ld_attention_bf16: empty problem");
-  LD_CHECK_ARG(nq <= q_rows && nkv <= kv_rows, "ld_attention_bf16: nq/nkv exceed buffer rows");
-  LD_CHECK_ARG(out_f32 == nullptr || lse != nullptr, "ld_attention_bf16: out_f32 requires lse");
+  LD_CHECK_ARG(q && shards && out, "ld_attention: null pointer");
+  LD_CHECK_ARG(n_shards >= 1 && n_shards <= kMaxShards, "ld_attention: 1..%d K/V shards, got %d", kMaxShards, n_shards);
+  LD_CHECK_ARG(batch > 0 && heads > 0 && nq > 0, "ld_attention: empty problem");
+  LD_CHECK_ARG(nq <= q_rows, "ld_attention: nq exceeds the q buffer rows");
+  LD_CHECK_ARG(out_f32 == nullptr || lse != nullptr, "ld_attention: out_f32 requires lse");
   const int BH = batch * heads;
-  CUtensorMap tq, tk, tv;
+  AttnShards sh;
+  memset(&sh, 0, sizeof(sh));
   const uint32_t box[3] = {64, 128, 1};
   {
     // dims limited to the rows actually used so TMA zero-fills the tail
     const uint64_t dims[3] = {64, (uint64_t)nq, (uint64_t)BH};
     const uint64_t str[2] = {128, (uint64_t)q_rows * 128};
-    rc = make_tmap_bf16(&tq, q, 3, dims, str, box);
+    rc = make_tmap_bf16(&sh.q, q, 3, dims, str, box);
     if (rc != LD_OK) return rc;
   }
-  {
-    const uint64_t dims[3] = {64, (uint64_t)nkv, (uint64_t)BH};
-    const uint64_t str[2] = {128, (uint64_t)kv_rows * 128};
-    rc = make_tmap_bf16(&tk, k, 3, dims, str, box);
+  int n_sub = 0;
+  for (int s = 0; s < n_shards; ++s) {
+    const ld_kv_shard& d = shards[s];
+    LD_CHECK_ARG(d.k && d.v && d.nkv > 0 && d.nkv <= d.kv_rows, "ld_attention: bad K/V shard %d", s);
+    const uint64_t dims[3] = {64, (uint64_t)d.nkv, (uint64_t)BH};
+    const uint64_t str[2] = {128, (uint64_t)d.kv_rows * 128};
+    rc = make_tmap_bf16(&sh.k[s], d.k, 3, dims, str, box);
     if (rc != LD_OK) return rc;
-    rc = make_tmap_bf16(&tv, v, 3, dims, str, box);
+    rc = make_tmap_bf16(&sh.v[s], d.v, 3, dims, str, box);
     if (rc != LD_OK) return rc;
+    sh.nkv[s] = d.nkv;
+    sh.ready[s] = d.ready_flag;
+    sh.ready_val[s] = d.ready_value;
+    n_sub += (d.nkv + 63) / 64;
   }
+  LD_CHECK_ARG(n_sub <= kMaxSub, "ld_attention: %d keys-blocks exceed the limit of %d (131072 keys)", n_sub, kMaxSub);
+  sh.n = n_shards;
+  sh.n_sub = n_sub;
+  rc = status_word(&sh.status);
+  if (rc != LD_OK) return rc;
+  // a peer that never delivers must not hang the GPU: ~2 s at 1.9 GHz by default (LD_ATTN_WAIT_MS overrides; the
+  // single-GPU multi-process tests, where the ranks time-slice one device, use a longer bound)
+  static long long wait_cycles = 0;
+  if (wait_cycles == 0) {
+    const char* e = getenv("LD_ATTN_WAIT_MS");
+    const long long ms = e ? atoll(e) : 2000;
+    wait_cycles = (ms > 0 ? ms : 2000) * 2000000LL;
+  }
+  sh.wait_cycles = wait_cycles;
   AttnParams prm;
   prm.out = (bf16*)out;
   prm.lse = lse;
   prm.out_f32 = out_f32;
   prm.heads = heads;
   prm.nq = nq;
-  prm.nkv = nkv;
   prm.prof = nullptr;
-  prm.redo = nullptr;
-  prm.redo_only = 0;
+  prm.exact_only = 0;
   prm.q = (const bf16*)q;
   prm.q_rows = q_rows;
   prm.scale_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
   const int grid = BH * ((nq + 255) / 256);
-  // variant 0: attn4_kernel (fixed first-block reference maximum) + exact fix-up launch   1: exact kernel only
-  //         (attn3_kernel: per-block maxima, lazy rescaling)   2 / 3: attn4 with every 4th / 3rd exponential on the
-  //         FMA pipe (polynomial)   4 / 5 / 6: attn4 with packed f32x2 FMA / ADD and every 4th / 8th / no polynomial
   cudaStream_t st = (cudaStream_t)stream;
+  // variant 0: fast path (5 of 16 column pairs on the FMA-pipe polynomial) with the exact path as in-launch fallback
+  //         1: exact path only (per-block maxima, lazy rescaling)
+  //         2 / 3 / 4: fast path with 0 / 4 / 6 of 16 pairs on the polynomial   5: variant 0 with truncating bf16 pack
   switch (variant) {
-    case 1:
+    case 0:
       if (g_attn_prof != nullptr) {
         prm.prof = g_attn_prof;
-        return launch_attn3<0, true>(tq, tk, tv, prm, grid, st);
+        return launch_attn5<5, false, true>(sh, prm, grid, st);
       }
-      return launch_attn3<0>(tq, tk, tv, prm, grid, st);
-    case 0:
-    case 2:
-    case 3:
-    case 4:
-    case 5:
-    case 6: {
-      rc = redo_buffer(grid, &prm.redo);
-      if (rc != LD_OK) return rc;
-      if (variant == 0 && g_attn_prof != nullptr) {
-        prm.prof = g_attn_prof;
-        rc = launch_attn4<0, true>(tk, tv, prm, grid, st);
-      } else if (variant == 0) {
-        rc = launch_attn4<0>(tk, tv, prm, grid, st);
-      } else if (variant == 2) {
-        rc = launch_attn4<4>(tk, tv, prm, grid, st);
-      } else if (variant == 3) {
-        rc = launch_attn4<3>(tk, tv, prm, grid, st);
-      } else if (variant == 4) {
-        rc = launch_attn4<4, false, true>(tk, tv, prm, grid, st);   // packed f32x2 + every 4th polynomial
-      } else if (variant == 5) {
-        rc = launch_attn4<8, false, true>(tk, tv, prm, grid, st);   // packed f32x2 + every 8th polynomial
-      } else {
-        rc = launch_attn4<0, false, true>(tk, tv, prm, grid, st);   // packed f32x2, all MUFU
-      }
-      if (rc != LD_OK) return rc;
-      prm.prof = nullptr;
-      prm.redo_only = 1;   // exact kernel, flagged CTAs only (all others exit at once)
-      return launch_attn3<0>(tq, tk, tv, prm, grid, st);
-    }
+      return launch_attn5<5, false>(sh, prm, grid, st);
+    case 1:
+      prm.exact_only = 1;
+      return launch_attn5<5, false>(sh, prm, grid, st);
+    case 2: return launch_attn5<0, false>(sh, prm, grid, st);
+    case 3: return launch_attn5<4, false>(sh, prm, grid, st);
+    case 4: return launch_attn5<6, false>(sh, prm, grid, st);
+    case 5: return launch_attn5<5, true>(sh, prm, grid, st);
     default:
-      set_error("ld_attention_bf16: unknown variant %d", variant);
+      set_error("ld_attention: unknown variant %d", variant);
       return LD_ERR_ARG;
   }
+}
+
+extern "C" int ld_attention_bf16(const void* q, const void* k, const void* v, void* out, float* lse, float* out_f32,
+                                 int batch, int heads, int nq, int q_rows, int nkv, int kv_rows, int variant,
+                                 void* stream) {
+  LD_CHECK_ARG(q && k && v && out, "ld_attention_bf16: null pointer");
+  LD_CHECK_ARG(nkv > 0 && nkv <= kv_rows, "ld_attention_bf16: nkv exceeds the buffer rows");
+  ld_kv_shard one;
+  one.k = k;
+  one.v = v;
+  one.nkv = nkv;
+  one.kv_rows = kv_rows;
+  one.ready_flag = nullptr;
+  one.ready_value = 0;
+  return ld_attention_shards_bf16(q, &one, 1, out, lse, out_f32, batch, heads, nq, q_rows, variant, stream);
 }
 
 extern "C" int ld_attention_merge(float* o_acc, float* lse_acc, const float* o_new, const float* lse_new, void* out_bf16,

@@ -83,16 +83,33 @@ int ld_gemm_bf16(const ld_gemm_args* args, void* stream);
 /* ---- full (non-causal) self-attention, head_dim 64, flash-style online softmax on tcgen05 ------------- */
 /* q: [BH, q_rows, 64], k/v: [BH, kv_rows, 64] bf16; scores are scaled by 1/sqrt(64) inside the kernel.
    Uses q rows [0,nq) and kv rows [0,nkv).  out: bf16 [B, nq, heads*64] (token-major, ready for `dense`).
-   variant: 0 = default (fixed per-row reference maximum + exact fix-up launch for overflowed CTAs), 1 = exact kernel
-   only (per-block maxima, lazy rescaling), 2 / 3 = default with every 4th / 3rd exponential as an FMA-pipe polynomial,
-   4 / 5 / 6 = default with packed f32x2 FMA / ADD and every 4th / 8th / no polynomial (experiments; slower today).
-   Keeps one process-wide scratch array of per-CTA redo flags (allocated on first use), so concurrent calls must be
-   on the same stream.
+   variant: 0 = default (one fixed reference maximum per row, 5 of 16 exponential pairs on the FMA pipe, row sums on the
+   tensor core; CTAs whose reference overflowed re-run through the exact path inside the same launch), 1 = exact path only
+   (per-block maxima, lazy rescaling), 2 / 3 / 4 = default with 0 / 4 / 6 of 16 pairs on the FMA pipe, 5 = default with a
+   truncating bf16 pack (tuning variants).
    If lse != NULL also writes fp32 log2-sum-exp [BH, nq] and, when out_f32 != NULL, the normalised fp32 output
-   [BH, nq, 64] (used by the ring merge).  Replaces SAT attention_fn_default -> F.scaled_dot_product_attention
-   reached through dit_video_concat.py:655-664. */
+   [BH, nq, 64].  Replaces SAT attention_fn_default -> F.scaled_dot_product_attention reached through
+   dit_video_concat.py:655-664. */
 int ld_attention_bf16(const void* q, const void* k, const void* v, void* out, float* lse, float* out_f32,
                       int batch, int heads, int nq, int q_rows, int nkv, int kv_rows, int variant, void* stream);
+
+/* The same attention over K/V given as 1..4 SHARDS of the key sequence (ring sequence parallelism: the local shard and
+   the shards the peers' copy engines deliver into IPC-mapped buffers, csrc/peer_ring.cu).  ONE launch walks all shards,
+   accumulating in TMEM.  A shard with ready_flag != NULL is still in flight when the kernel starts: the kernel's TMA
+   producer polls the 32-bit device word until (int32)(*ready_flag - ready_value) >= 0 (acquire, system scope) before its
+   first load from that shard.  A wait that lasts longer than ~2 s gives up and raises bit 0 of the status word
+   (ld_attention_status) instead of hanging the GPU.  The reference has no sequence parallelism. */
+typedef struct ld_kv_shard {
+  const void* k;              /* [BH, kv_rows, 64] bf16 */
+  const void* v;
+  int32_t nkv, kv_rows;
+  const uint32_t* ready_flag; /* device pointer or NULL */
+  uint32_t ready_value;
+} ld_kv_shard;
+int ld_attention_shards_bf16(const void* q, const ld_kv_shard* shards, int n_shards, void* out, float* lse, float* out_f32,
+                             int batch, int heads, int nq, int q_rows, int variant, void* stream);
+/* copies the per-device status word of the shard waits to *host_out (synchronising); reset != 0 clears it */
+int ld_attention_status(unsigned int* host_out, int reset);
 
 /* merge two partial attention results (ring hop):  (o_acc, lse_acc) <- merge((o_acc, lse_acc), (o_new, lse_new)).
    o_*: fp32 [BH, nq, 64]; lse_*: fp32 [BH, nq].  If out_bf16 != NULL also writes bf16 [B, nq, heads*64]. */

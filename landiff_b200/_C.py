@@ -37,6 +37,13 @@ class GemmArgs(C.Structure):
     ]
 
 
+class KvShard(C.Structure):
+    """Mirror of `ld_kv_shard` (include/landiff_b200.h)."""
+
+    _fields_ = [("k", C.c_void_p), ("v", C.c_void_p), ("nkv", C.c_int32), ("kv_rows", C.c_int32),
+                ("ready_flag", C.c_void_p), ("ready_value", C.c_uint32)]
+
+
 # name -> (restype, argtypes); the CPU test-suite checks every one of these is exported.
 _vp, _i, _f, _i64, _fp = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_void_p
 SIGNATURES = {
@@ -45,6 +52,8 @@ SIGNATURES = {
     "ld_device_check": (C.c_int, [C.POINTER(C.c_int)]),
     "ld_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "ld_attention_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ld_attention_shards_bf16": (C.c_int, [_vp, C.POINTER(KvShard), _i, _vp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
+    "ld_attention_status": (C.c_int, [C.POINTER(C.c_uint), _i]),
     "ld_attention_merge": (C.c_int, [_fp, _fp, _fp, _fp, _vp, _i, _i, _i, _vp]),
     "ld_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
     "ld_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),

@@ -157,6 +157,63 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, nq: Optional
     return out
 
 
+def attention_shards(q: torch.Tensor, shards, *, nq: Optional[int] = None, out: Optional[torch.Tensor] = None,
+                     lse: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
+    """softmax(q [k_0|k_1|...]^T / 8) [v_0|v_1|...] with K/V given as 1..4 shards of the key sequence, ONE launch.
+    `shards`: sequence of (k, v) or (k, v, nkv) or (k, v, nkv, ready_flag_ptr, ready_value) with k, v [B, H, rows, 64]
+    bf16; a shard with a ready flag (device address of a u32) may still be in flight: the kernel waits for
+    (int32)(*flag - value) >= 0 before reading it (ring sequence parallelism, landiff_b200/parallel.py)."""
+    _chk(q, BF16, "q")
+    if q.dim() != 4 or q.shape[-1] != 64:
+        raise ValueError("attention: q must be [B, H, rows, 64]")
+    B, H, q_rows, _ = q.shape
+    nq = q_rows if nq is None else nq
+    if not 0 < nq <= q_rows:
+        raise ValueError(f"attention: nq={nq} outside the q buffer ({q_rows} rows)")
+    if not 1 <= len(shards) <= 4:
+        raise ValueError(f"attention: 1..4 K/V shards, got {len(shards)}")
+    arr = (_C.KvShard * len(shards))()
+    for i, sh in enumerate(shards):
+        k, v = sh[0], sh[1]
+        for n_, t_ in (("k", k), ("v", v)):
+            _chk(t_, BF16, n_)
+            if t_.dim() != 4 or t_.shape[-1] != 64 or t_.shape[:2] != q.shape[:2]:
+                raise ValueError(f"attention: shard {i} {n_} {tuple(t_.shape)} does not match q {tuple(q.shape)}")
+        if k.shape != v.shape:
+            raise ValueError(f"attention: shard {i} k / v shapes differ")
+        nkv = k.shape[2] if len(sh) < 3 or sh[2] is None else int(sh[2])
+        if not 0 < nkv <= k.shape[2]:
+            raise ValueError(f"attention: shard {i} nkv={nkv} outside its buffer ({k.shape[2]} rows)")
+        arr[i].k, arr[i].v, arr[i].nkv, arr[i].kv_rows = k.data_ptr(), v.data_ptr(), nkv, k.shape[2]
+        if len(sh) >= 5 and sh[3]:
+            arr[i].ready_flag, arr[i].ready_value = int(sh[3]), int(sh[4]) & 0xFFFFFFFF
+    if out is None:
+        out = torch.empty((B, nq, H * 64), dtype=BF16, device=q.device)
+    _chk(out, BF16, "out")
+    if out.numel() != B * nq * H * 64:
+        raise ValueError(f"attention: out must hold [B, nq, H*64] = {B * nq * H * 64} elements, got {out.numel()}")
+    if lse is not None:
+        _chk(lse, F32, "lse")
+        if lse.numel() != B * H * nq:
+            raise ValueError("attention: lse must hold [B*H, nq] elements")
+    if out_f32 is not None:
+        _chk(out_f32, F32, "out_f32")
+        if lse is None or out_f32.numel() != B * H * nq * 64:
+            raise ValueError("attention: out_f32 must hold [B*H, nq, 64] elements and needs lse")
+    check(_C.load().ld_attention_shards_bf16(q.data_ptr(), arr, len(shards), out.data_ptr(), _ptr(lse), _ptr(out_f32),
+                                             B, H, nq, q_rows, variant, _stream()), "ld_attention_shards_bf16")
+    return out
+
+
+def attention_status(reset: bool = True) -> int:
+    """Status word of the in-kernel shard waits on the current device (bit 0: a wait timed out).  Synchronises."""
+    w = C.c_uint(0)
+    rc = _C.load().ld_attention_status(C.byref(w), int(reset))
+    if rc != 0:
+        check(rc, "ld_attention_status")
+    return w.value
+
+
 def attention_merge(o_acc, lse_acc, o_new, lse_new, out_bf16, batch, heads, nq) -> None:
     for t_ in (o_acc, lse_acc, o_new, lse_new):
         _chk(t_, F32, "merge operand")

@@ -6,9 +6,10 @@ Two orthogonal axes:
     bf16 network outputs are exchanged (1.1 MB) and every rank applies the fused CFG + DPM++ update redundantly
     with identical RNG state.
   * ring sequence parallelism (x2 / x4) over the token axis: every op except attention is row-local; for attention
-    the K|V shard [2, B, H, N/sp, 64] rotates around the ring with NCCL send/recv on a side stream, overlapped with
-    the attention tiles of the shard already present, and the per-shard partial results are merged by their
-    log-sum-exp (`ld_attention_merge`).  Ulysses is not applicable (30 heads do not divide by 4 or 8).
+    every rank pushes its K|V shard [2, B, H, N/sp, 64] to its peers with copy-engine peer copies over NVLink on a side
+    stream, and ONE attention launch walks the local shard and then the peers' shards as they arrive (the kernel polls
+    the arrival flags; accumulation stays in TMEM, nothing is merged afterwards).  Ulysses is not applicable (30 heads
+    do not divide by 4 or 8).
 rank = cfg_rank * sp_size + sp_rank.   world 1: none · 2: CFG · 4: CFG x SP2 · 8: CFG x SP4.
 """
 from __future__ import annotations
@@ -98,139 +99,89 @@ def ring_attention_generic(q, kv_local, sp_size: int, sp_rank: int, exchange: Ca
 
 
 class RingAttention:
-    """GPU ring: attached to a DiffusionTransformer as `.ring`; called with the layer workspace.
+    """Sequence-parallel attention of one rank, attached to a DiffusionTransformer as `.ring` and called with the layer
+    workspace.  Every rank needs every peer's K|V shard once per layer; the attention itself is ONE launch over all
+    shards (`ops.attention_shards`, accumulating in TMEM — no per-hop launches, no partial-result merges).
 
-    transport "nccl" (default): batch_isend_irecv on a high-priority side stream.  transport "dma" (or
-    LD_RING_TRANSPORT=dma): copy-engine peer copies into IPC-mapped buffers ordered by stream memory operations
-    (landiff_b200/dma_ring.py) — no SMs, which matters because the attention kernel leaves none free."""
+    transport "dma" (default; LD_RING_TRANSPORT overrides): the local shard is pushed to every peer by copy-engine peer
+    copies into IPC-mapped receive buffers (landiff_b200/dma_ring.py) on a side stream — no SMs, which matters because
+    the attention kernel leaves none free — and the kernel polls the per-shard arrival flags itself, so it starts on the
+    local shard immediately and the transfers hide behind it.
+    transport "nccl": one `all_gather_into_tensor` of the shards on the side stream, the launch waits for all of it
+    (portable fallback without CUDA IPC; the transfer is not overlapped)."""
 
     def __init__(self, layout: Layout, sp_group, device, transport: Optional[str] = None):
         import os
 
         self.layout, self.group, self.device = layout, sp_group, device
-        self.transport = (transport or os.environ.get("LD_RING_TRANSPORT", "nccl")).lower()
+        self.transport = (transport or os.environ.get("LD_RING_TRANSPORT", "dma")).lower()
         if self.transport not in ("nccl", "dma"):
             raise ValueError(f"unknown ring transport {self.transport!r}")
-        # High priority: the attention kernel fills every SM (640 threads x ~100 registers), so NCCL's send/recv CTAs only
-        # run when an SM drains; with priority they take the first free slots instead of queueing behind the
-        # remaining attention CTAs (measured with the default priority: 34 MB hops at 129 GB/s, not hidden at sp = 4).
+        if not 2 <= layout.sp_size <= 4:
+            raise ValueError(f"sequence-parallel groups of 2..4 ranks are supported, got {layout.sp_size}")
         self.comm_stream = torch.cuda.Stream(device=device, priority=-1)
-        ranks = layout.sp_group_ranks()
-        self.next_rank = ranks[(layout.sp_rank + 1) % layout.sp_size]
-        self.prev_rank = ranks[(layout.sp_rank - 1) % layout.sp_size]
         self._bufs = {}
         self._peer = {}
 
-    def _buffers(self, ws):
-        key = id(ws)
-        b = self._bufs.get(key)
-        if b is None:
-            kv = ws["kv"]
-            B, H, R = ws["q"].shape[:3]
-            f = lambda *s: torch.empty(*s, dtype=torch.float32, device=kv.device)
-            b = dict(o_acc=f(B * H, R, 64), lse_acc=f(B * H, R), o_new=f(B * H, R, 64), lse_new=f(B * H, R))
-            if self.transport == "nccl":
-                b["ring"] = [torch.empty_like(kv), torch.empty_like(kv)]
-            self._bufs[key] = b
-        return b
-
-    def _peer_ring(self, kv):
+    def _peer_gather(self, kv):
         key = (tuple(kv.shape), kv.dtype)
-        pr = self._peer.get(key)
-        if pr is None:
-            from .dma_ring import PeerRing
+        pg = self._peer.get(key)
+        if pg is None:
+            from .dma_ring import PeerGather
 
-            pr = PeerRing(self.group, self.layout.sp_group_ranks(), self.layout.rank, kv.shape, kv.dtype, kv.device)
-            self._peer[key] = pr
-        return pr
+            pg = PeerGather(self.group, self.layout.sp_group_ranks(), self.layout.rank, kv.shape, kv.dtype, kv.device)
+            self._peer[key] = pg
+        return pg
 
     def attention(self, ws, variant: int = 0):
         if self.transport == "dma":
             return self._attention_dma(ws, variant)
         from . import ops
 
-        sp = self.layout.sp_size
-        b = self._buffers(ws)
-        q, out = ws["q"], ws["attn"]
-        B, H, R = q.shape[:3]
-        cur = ws["kv"]
-        compute = torch.cuda.current_stream()
-        for hop in range(sp):
-            reqs = None
-            nxt = None
-            if hop < sp - 1:
-                nxt = b["ring"][hop % 2]
-                ready = torch.cuda.Event()
-                ready.record(compute)  # `cur` is complete on the compute stream (QKV GEMM / previous receive)
-                self.comm_stream.wait_event(ready)
-                with torch.cuda.stream(self.comm_stream):
-                    ops_ = [dist.P2POp(dist.isend, cur, self.next_rank, group=self.group),
-                            dist.P2POp(dist.irecv, nxt, self.prev_rank, group=self.group)]
-                    reqs = dist.batch_isend_irecv(ops_)
-            if hop == 0:
-                ops.attention(q, cur[0], cur[1], out=out, lse=b["lse_acc"], out_f32=b["o_acc"], variant=variant)
-            else:
-                ops.attention(q, cur[0], cur[1], out=out, lse=b["lse_new"], out_f32=b["o_new"], variant=variant)
-                ops.attention_merge(b["o_acc"], b["lse_acc"], b["o_new"], b["lse_new"], out if hop == sp - 1 else None,
-                                    B, H, R)
-            if reqs is not None:
-                with torch.cuda.stream(self.comm_stream):
-                    for r in reqs:
-                        r.wait()
-                done = torch.cuda.Event()
-                done.record(self.comm_stream)
-                compute.wait_event(done)
-                cur = nxt
-
-    def _attention_dma(self, ws, variant: int):
-        """Same schedule with the copy-engine transport: at hop h this rank forwards the shard it holds into the
-        downstream rank's recv[h % 2] while it attends to it; the shard for hop h+1 arrives in its own recv[h % 2]."""
-        from . import ops
-
-        sp = self.layout.sp_size
-        b = self._buffers(ws)
-        q, out = ws["q"], ws["attn"]
-        B, H, R = q.shape[:3]
+        sp, me = self.layout.sp_size, self.layout.sp_rank
         kv = ws["kv"]
-        pr = self._peer_ring(kv)
+        gathered = self._bufs.get(id(ws))
+        if gathered is None:
+            gathered = self._bufs[id(ws)] = torch.empty((sp,) + tuple(kv.shape), dtype=kv.dtype, device=kv.device)
         compute = torch.cuda.current_stream()
-        cur, cur_j, cur_T = kv, -1, 0     # shard held at this hop; the recv buffer it lives in (-1: local kv)
-        for hop in range(sp):
-            sent_T = None
-            if hop < sp - 1:
-                j = hop % 2
-                if hop == 0:
-                    ready = torch.cuda.Event()
-                    ready.record(compute)        # local K|V written by the QKV GEMM
-                    self.comm_stream.wait_event(ready)
-                else:
-                    pr.wait_arrival(cur_j, cur_T, self.comm_stream)   # forward as soon as it has landed
-                sent_T = pr.push(cur, j, self.comm_stream)
-            if hop > 0:
-                pr.wait_arrival(cur_j, cur_T, compute)
-            if hop == 0:
-                ops.attention(q, cur[0], cur[1], out=out, lse=b["lse_acc"], out_f32=b["o_acc"], variant=variant)
-            else:
-                ops.attention(q, cur[0], cur[1], out=out, lse=b["lse_new"], out_f32=b["o_new"], variant=variant)
-                ops.attention_merge(b["o_acc"], b["lse_acc"], b["o_new"], b["lse_new"], out if hop == sp - 1 else None,
-                                    B, H, R)
-            if hop < sp - 1:
-                # the next shard to attend to arrives in my recv[hop % 2] with the same id my own push carries
-                # (every rank numbers its transfers identically)
-                nxt_j, nxt_T = hop % 2, sent_T
-            if hop > 0:
-                # recv[cur_j] has been read by the attention above AND (if forwarded) by the push on the comm stream
-                if hop < sp - 1:
-                    fwd = torch.cuda.Event()
-                    fwd.record(self.comm_stream)
-                    compute.wait_event(fwd)
-                pr.release(cur_j, cur_T, compute)
-            if hop < sp - 1:
-                cur, cur_j, cur_T = pr.recv[nxt_j], nxt_j, nxt_T
-        # the QKV GEMM of the next layer overwrites ws["kv"]: the push of hop 0 must have read it
+        ready = torch.cuda.Event()
+        ready.record(compute)              # local K|V written by the QKV GEMM
+        self.comm_stream.wait_event(ready)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_gather_into_tensor(gathered.view(-1), kv.view(-1), group=self.group)
         done = torch.cuda.Event()
         done.record(self.comm_stream)
         compute.wait_event(done)
+        order = [(me - j) % sp for j in range(sp)]      # same key order as the dma transport: local, rank-1, rank-2, ...
+        ops.attention_shards(ws["q"], [(gathered[r][0], gathered[r][1]) for r in order], out=ws["attn"], variant=variant)
+
+    def _attention_dma(self, ws, variant: int):
+        from . import ops
+
+        kv = ws["kv"]
+        pg = self._peer_gather(kv)
+        compute = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(compute)              # local K|V written by the QKV GEMM
+        self.comm_stream.wait_event(ready)
+        T = pg.push_all(kv, self.comm_stream)
+        ops.attention_shards(ws["q"], pg.kernel_shards(kv, T), out=ws["attn"], variant=variant)
+        pg.release_all(T, compute)
+        # the QKV GEMM of the next layer overwrites ws["kv"]: the pushes must have read it
+        done = torch.cuda.Event()
+        done.record(self.comm_stream)
+        compute.wait_event(done)
+
+
+def _all_reduce_sum(buf: torch.Tensor, group) -> None:
+    """Sum all-reduce in place.  gloo (CPU tests, single-GPU multi-process tests) has no bf16 reduction: stage through
+    fp32 there — every element is x + 0 + ... + 0, exact in either type."""
+    if buf.dtype == torch.bfloat16 and dist.get_backend(group) == "gloo":
+        tmp = buf.float()
+        dist.all_reduce(tmp, group=group)
+        buf.copy_(tmp)
+    else:
+        dist.all_reduce(buf, group=group)
 
 
 class CFGGroup:
@@ -257,7 +208,7 @@ class CFGGroup:
         else:
             buf[row].copy_(torch.where(owned_mask, net_local[0], torch.zeros_like(net_local[0])))
         if self.layout.world > 1:
-            dist.all_reduce(buf, group=self.group)
+            _all_reduce_sum(buf, self.group)
         return buf
 
     def evaluate(self, network, x, timestep: float, ctx2, **kwargs):
@@ -281,7 +232,7 @@ class CFGGroup:
                 self._buf = torch.zeros(net.shape, dtype=net.dtype, device=net.device)
             buf = self._buf
             buf.copy_(torch.where(own, net, torch.zeros_like(net)))
-            dist.all_reduce(buf, group=self.group)
+            _all_reduce_sum(buf, self.group)
             return buf[0:1], buf[1:2]
         return net[0:1], net[1:2]
 

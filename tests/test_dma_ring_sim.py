@@ -1,14 +1,18 @@
-"""CPU: discrete-event simulation of the copy-engine ring protocol (landiff_b200/dma_ring.py + RingAttention._attention_dma).
+"""CPU: discrete-event simulation of the copy-engine K|V exchange protocol (landiff_b200/dma_ring.py +
+RingAttention._attention_dma).
 
-The REAL host code runs for every rank of a ring (PeerRing.push / wait_arrival / release and the hop schedule); only the
-three C-ABI calls it makes (stream wait-value, stream write-value, async copy), torch's CUDA streams / events and the
-attention launch are replaced by queue entries.  A simulator then executes the per-stream queues in random
-interleavings with the semantics of the real primitives (in-order streams, wait blocks its stream until the flag is
-reached, a copy moves whatever the source holds WHEN IT EXECUTES) and checks, for rings of 2, 3, 4 and 8 ranks over
-several back-to-back calls (layers) whose K|V buffer is overwritten each call:
+The REAL host code runs for every rank of a sequence-parallel group (PeerGather.push_all / kernel_shards / release_all
+and the per-layer schedule); only the three C-ABI calls it makes (stream wait-value, stream write-value, async copy),
+torch's CUDA streams / events and the attention launch are replaced by queue entries.  The multi-shard attention kernel
+is modelled as what it does: for every shard in order, wait for the shard's arrival flag (the in-kernel poll blocks that
+kernel, hence its stream), then read it.  A simulator then executes the per-stream queues in random interleavings with
+the semantics of the real primitives (in-order streams, a wait blocks its stream until the flag is reached, a copy moves
+whatever the source holds WHEN IT EXECUTES) and checks, for groups of 2, 3 and 4 ranks over several back-to-back calls
+(layers) whose K|V buffer is overwritten each call:
   * no deadlock under any explored interleaving,
-  * every attention reads exactly the shard the ring schedule prescribes, of the right call — i.e. no receive buffer
-    and no local K|V buffer is overwritten before its last reader has run, and nothing is read before it has landed.
+  * every attention reads exactly the shards the schedule prescribes (local, rank-1, rank-2, ...), of the right call —
+    i.e. no receive buffer and no local K|V buffer is overwritten before its last reader has run, and nothing is read
+    before it has landed.
 """
 import random
 
@@ -104,71 +108,76 @@ class FakeEvent:
         FakeEvent.sim.enqueue(stream.cuda_stream, ("record", self.token))
 
 
-def build_ring(sim, sp):
-    """Per rank: a RingAttention in dma mode whose PeerRing is wired to its neighbours through simulated memory."""
+def build_group(sim, sp):
+    """Per rank: a RingAttention in dma mode whose PeerGather is wired to its peers through simulated memory."""
     lib = FakeLib(sim)
     shape = (2, 4)
-    recv = [[torch.zeros(shape) for _ in range(2)] for _ in range(sp)]
-    flag_base = [1000 * (r + 1) for r in range(sp)]          # fake device addresses of each rank's flag array
-    rings = []
+    recv = [[torch.zeros(shape) for _ in range(sp - 1)] for _ in range(sp)]
+    flag_base = [1000 * (r + 1) for r in range(sp)]          # fake device addresses of each rank's flag page
+    ranks = []
     for r in range(sp):
         for t in recv[r]:
             sim.tensors[t.data_ptr()] = t
-        pr = object.__new__(dma_ring.PeerRing)
-        pr.lib, pr.device, pr.nbytes, pr.shape, pr.dtype = lib, "cpu", 2 * 4 * 4, shape, torch.float32
-        pr._flags_ptr = flag_base[r]
-        down, up = (r + 1) % sp, (r - 1) % sp
-        pr._down_recv = [t.data_ptr() for t in recv[down]]
-        pr._down_flags, pr._up_flags = flag_base[down], flag_base[up]
-        pr.recv = recv[r]
-        pr.next_id, pr.last_sent = 1, [0, 0]
+        pg = object.__new__(dma_ring.PeerGather)
+        pg.lib, pg.device, pg.nbytes, pg.shape, pg.dtype = lib, "cpu", 2 * 4 * 4, shape, torch.float32
+        pg.n, pg.me = sp, r
+        pg._flags_ptr = flag_base[r]
+        pg._peer_recv = {d: recv[(r + d) % sp][d - 1].data_ptr() for d in range(1, sp)}
+        pg._peer_flags = {d: flag_base[(r + d) % sp] for d in range(1, sp)}
+        pg.recv = recv[r]
+        pg.next_id, pg.last_sent = 1, 0
         ra = object.__new__(parallel.RingAttention)
         ra.layout = parallel.Layout(sp, r, 1, sp)
         ra.group, ra.device, ra.transport = None, "cpu", "dma"
         ra.comm_stream = FakeStream(sim, f"comm{r}")
         ra.compute_stream = FakeStream(sim, f"compute{r}")
         ra._bufs, ra._peer = {}, {}
-        ra._peer_ring = lambda kv, pr=pr: pr
+        ra._peer_gather = lambda kv, pg=pg: pg
         kv = torch.zeros(shape)
         sim.tensors[kv.data_ptr()] = kv
         ws = dict(q=torch.zeros(1, 1, 1, 64), kv=kv, attn=torch.zeros(1, 1, 64))
-        rings.append((ra, ws))
-    return rings
+        ranks.append((ra, ws, pg))
+    return ranks
 
 
-def simulate(sp, seed, monkeypatch, attention_dma=None, n_calls=5):
+def simulate(sp, seed, monkeypatch, attention_dma=None, n_calls=5, mutate=None):
     """Host phase for every rank (all calls enqueued up front), then one random interleaving.  Returns the read log;
     raises AssertionError on deadlock."""
     from landiff_b200 import ops
 
     sim = Sim()
     FakeEvent.sim = sim
-    rings = build_ring(sim, sp)
+    ranks = build_group(sim, sp)
     current = {}
     monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: current["ra"].compute_stream)
     monkeypatch.setattr(dma_ring, "check", lambda rc, what: None)
 
-    def fake_attention(q, k, v, out=None, lse=None, out_f32=None, variant=0):
-        ra, call, hop = current["ra"], current["call"], current["hop_counter"][0]
-        current["hop_counter"][0] += 1
+    def fake_attention_shards(q, shards, out=None, variant=0, **kw):
+        ra, call = current["ra"], current["call"]
         r = ra.layout.rank
+        for j, sh in enumerate(shards):
+            k = sh[0]
+            if len(sh) >= 5 and sh[3]:
+                sim.enqueue(ra.compute_stream.cuda_stream, ("wait_geq", sh[3], sh[4]))   # the kernel's poll of the flag
 
-        def read(k=k, r=r, call=call, hop=hop):
-            sim.log.append((r, call, hop, int(k.view(-1)[0]), int(k.view(-1)[1])))
+            def read(k=k, r=r, call=call, j=j):
+                sim.log.append((r, call, j, int(k.view(-1)[0]), int(k.view(-1)[1])))
 
-        sim.enqueue(ra.compute_stream.cuda_stream, ("call", read))
+            sim.enqueue(ra.compute_stream.cuda_stream, ("call", read))
 
-    monkeypatch.setattr(ops, "attention", fake_attention)
-    monkeypatch.setattr(ops, "attention_merge", lambda *a, **k: None)
+    monkeypatch.setattr(ops, "attention_shards", fake_attention_shards)
+    if mutate is not None:
+        for _, _, pg in ranks:
+            mutate(pg)
     # each call starts with the "QKV GEMM" overwriting the local K|V buffer with (rank, call); ranks are interleaved
     # arbitrarily on the host, calls stay in order
     order = [(c, r) for c in range(n_calls) for r in range(sp)]
     random.Random(seed).shuffle(order)
     order.sort(key=lambda cr: cr[0])
     for call, r in order:
-        ra, ws = rings[r]
-        current.update(ra=ra, call=call, hop_counter=[0])
+        ra, ws, _ = ranks[r]
+        current.update(ra=ra, call=call)
 
         def produce(kv=ws["kv"], r=r, call=call):
             kv.view(-1)[0], kv.view(-1)[1] = float(r), float(call)
@@ -180,48 +189,73 @@ def simulate(sp, seed, monkeypatch, attention_dma=None, n_calls=5):
 
 
 def reads_are_correct(log, sp, n_calls=5):
-    return len(log) == sp * n_calls * sp and all(s == (r - h) % sp and sc == c for r, c, h, s, sc in log)
+    return len(log) == sp * n_calls * sp and all(s == (r - j) % sp and sc == c for r, c, j, s, sc in log)
 
 
-@pytest.mark.parametrize("sp", [2, 3, 4, 8])
+@pytest.mark.parametrize("sp", [2, 3, 4])
 def test_protocol_is_safe_and_live_under_random_interleavings(sp, monkeypatch):
     for seed in range(12):
         log = simulate(sp, seed, monkeypatch)
-        for r, call, hop, shard, shard_call in log:
-            assert shard == (r - hop) % sp and shard_call == call, \
-                f"sp={sp} seed={seed}: rank {r} call {call} hop {hop} read shard {shard} of call {shard_call}"
+        for r, call, j, shard, shard_call in log:
+            assert shard == (r - j) % sp and shard_call == call, \
+                f"sp={sp} seed={seed}: rank {r} call {call} shard slot {j} read shard {shard} of call {shard_call}"
         assert reads_are_correct(log, sp)
 
 
-MUTATIONS = {
+def _strip_flags(pg):
+    orig = pg.kernel_shards
+    pg.kernel_shards = lambda kv, T: [sh[:3] for sh in orig(kv, T)]
+
+
+def _never_release(pg):
+    pg.release_all = lambda T, stream: None
+
+
+def _forget_previous_transfer(pg):
+    orig = pg.push_all
+
+    def push(src, comm):
+        T = orig(src, comm)
+        pg.last_sent = 0        # the next push will not wait for the consumption of this one
+        return T
+
+    pg.push_all = push
+
+
+SOURCE_MUTATIONS = {
     "no guard of the local K|V buffer at the end of a call":
         ("    done = torch.cuda.Event()\n    done.record(self.comm_stream)\n    compute.wait_event(done)\n", ""),
-    "release before the forwarding copy has read the buffer": ("                compute.wait_event(fwd)\n", ""),
-    "attention does not wait for the arrival": ("            pr.wait_arrival(cur_j, cur_T, compute)\n", "            pass\n"),
-    "forward does not wait for the arrival":
-        ("                pr.wait_arrival(cur_j, cur_T, self.comm_stream)   # forward as soon as it has landed\n",
-         "                pass\n"),
-    "buffers are never released": ("            pr.release(cur_j, cur_T, compute)\n", "            pass\n"),
+    "pushes do not wait for the QKV GEMM": ("    self.comm_stream.wait_event(ready)\n", ""),
+}
+OBJECT_MUTATIONS = {
+    "the kernel does not wait for the arrival flags": _strip_flags,
+    "receive buffers are never released": _never_release,
+    "a sender does not wait for the consumption of its previous shard": _forget_previous_transfer,
 }
 
 
-@pytest.mark.parametrize("name", sorted(MUTATIONS))
+@pytest.mark.parametrize("name", sorted(SOURCE_MUTATIONS) + sorted(OBJECT_MUTATIONS))
 def test_every_guard_of_the_schedule_is_necessary(name, monkeypatch):
-    """Mutation check: removing any single wait / release from RingAttention._attention_dma makes some interleaving
-    read the wrong shard or deadlock — so the simulation above really exercises those guards."""
+    """Mutation check: removing any single wait / release makes some interleaving read the wrong shard or deadlock — so
+    the simulation above really exercises those guards."""
     import inspect
     import textwrap
 
-    old, new = MUTATIONS[name]
-    src = textwrap.dedent(inspect.getsource(parallel.RingAttention._attention_dma))
-    assert old in src, "the mutation no longer matches the source; update MUTATIONS"
-    ns = {}
-    exec(src.replace(old, new), dict(vars(parallel), torch=torch), ns)
+    attention_dma, mutate = None, None
+    if name in SOURCE_MUTATIONS:
+        old, new = SOURCE_MUTATIONS[name]
+        src = textwrap.dedent(inspect.getsource(parallel.RingAttention._attention_dma))
+        assert old in src, "the mutation no longer matches the source; update SOURCE_MUTATIONS"
+        ns = {}
+        exec(src.replace(old, new), dict(vars(parallel), torch=torch), ns)
+        attention_dma = ns["_attention_dma"]
+    else:
+        mutate = OBJECT_MUTATIONS[name]
     broken = 0
     for sp in (2, 4):
         for seed in range(16):
             try:
-                broken += not reads_are_correct(simulate(sp, seed, monkeypatch, attention_dma=ns["_attention_dma"]), sp)
+                broken += not reads_are_correct(simulate(sp, seed, monkeypatch, attention_dma=attention_dma, mutate=mutate), sp)
             except AssertionError:      # deadlock
                 broken += 1
     assert broken > 0, name

@@ -96,7 +96,12 @@ def test_gemm_all_epilogues():
     report("gemm UNPATCHIFY", out, y.permute(0, 1, 4, 2, 5, 3, 6).reshape(B, T, Cc, 2 * Hp, 2 * Wp))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6])
+# lse is log2(sum of the bf16-rounded P the PV product uses) + reference: accumulated by the tensor core from the same
+# values as the numerator (fast path), so it carries their zero-mean rounding: up to ~1e-3 absolute on |lse| ~ 6 for short rows
+LSE_TOL = 2e-4
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_attention(variant):
     torch.manual_seed(1)
     for (B, H, nq, nkv) in [(1, 1, 128, 128), (1, 1, 256, 128), (1, 2, 300, 300), (2, 3, 886, 886), (1, 2, 500, 1000),
@@ -112,15 +117,17 @@ def test_attention(variant):
         report(f"attn v{variant} B{B} H{H} nq{nq} nkv{nkv}", out, ref.permute(0, 2, 1, 3).reshape(B, nq, H * 64))
         s = (q.float() @ k.float().transpose(-1, -2)) * 0.125
         lse_ref = torch.logsumexp(s, -1) * 1.4426950408889634
-        report("   lse", lse, lse_ref.view(B * H, nq), 1e-5)
+        report("   lse", lse, lse_ref.view(B * H, nq), LSE_TOL)
         report("   out_f32", of, ref.reshape(B * H, nq, 64))
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 4])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 5])
 def test_attention_overflow_fixup(variant):
     """One late key whose score is hundreds of log2-units above every row's first-block maximum: the fixed reference
-    maximum of attn4_kernel overflows, the CTA raises its redo flag and the exact kernel recomputes it.  Rows with a
-    negative projection on that key never overflow (mixed flagged / unflagged CTAs)."""
+    maximum of the fast path overflows (on MUFU columns: +inf; on polynomial columns: the clamped exponent field 255) and
+    the CTA re-runs its rows through the exact path inside the same launch.  Rows with a negative projection on that key
+    never overflow (mixed flagged / unflagged CTAs).  The key sits on column 2500 % 64 = 4 (pair 2: MUFU for KP = 5,
+    polynomial for none); a second run moves it to a polynomial column."""
     torch.manual_seed(5)
     B, H, nq, nkv = 1, 2, 1000, 3000
     q = torch.randn(B, H, nq, 64, device=dev)
@@ -129,16 +136,19 @@ def test_attention_overflow_fixup(variant):
     q[:, 0, :, 0] = q[:, 0, :, 0].abs() + 3.0          # head 0: every row overflows
     q[:, 1, :300, 0] = -(q[:, 1, :300, 0].abs() + 3.0)  # head 1: first 300 rows never do, the rest do
     q[:, 1, 300:, 0] = q[:, 1, 300:, 0].abs() + 3.0
-    k[:, :, 2500, :] = 0
-    k[:, :, 2500, 0] = 400.0
-    q, k, v = q.bfloat16(), k.bfloat16(), v.bfloat16()
-    lse = torch.zeros(B * H, nq, device=dev)
-    out = ops.attention(q, k, v, variant=variant, lse=lse)
-    torch.cuda.synchronize()
-    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
-    report(f"attn overflow v{variant}", out, ref.permute(0, 2, 1, 3).reshape(B, nq, H * 64))
-    s = (q.float() @ k.float().transpose(-1, -2)) * 0.125
-    report("   lse", lse, (torch.logsumexp(s, -1) * 1.4426950408889634).view(B * H, nq), 1e-5)
+    q, v = q.bfloat16(), v.bfloat16()
+    for key in (2500, 2496, 2561):     # columns 4 (MUFU pair for KP = 5), 0 (polynomial pair), 1 (second lane of a polynomial pair)
+        kk = k.clone()
+        kk[:, :, key, :] = 0
+        kk[:, :, key, 0] = 400.0
+        kk = kk.bfloat16()
+        lse = torch.zeros(B * H, nq, device=dev)
+        out = ops.attention(q, kk, v, variant=variant, lse=lse)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.scaled_dot_product_attention(q.float(), kk.float(), v.float())
+        report(f"attn overflow v{variant} key {key}", out, ref.permute(0, 2, 1, 3).reshape(B, nq, H * 64))
+        s = (q.float() @ kk.float().transpose(-1, -2)) * 0.125
+        report("   lse", lse, (torch.logsumexp(s, -1) * 1.4426950408889634).view(B * H, nq), LSE_TOL)
 
 
 @pytest.mark.parametrize("k0", [40.0, 90.0, 150.0])
@@ -162,7 +172,88 @@ def test_attention_late_dominant_key_without_overflow(k0):
     ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
     report(f"attn dominant key {k0}", out, ref.permute(0, 2, 1, 3).reshape(B, nq, H * 64))
     s = (q.float() @ k.float().transpose(-1, -2)) * 0.125
-    report("   lse", lse, (torch.logsumexp(s, -1) * 1.4426950408889634).view(B * H, nq), 1e-5)
+    report("   lse", lse, (torch.logsumexp(s, -1) * 1.4426950408889634).view(B * H, nq), LSE_TOL)
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_attention_over_kv_shards_equals_monolithic(variant):
+    """ONE launch over 2-4 K/V shards (ragged shard lengths: box tails of 1 and 2 sub-blocks, a shard shorter than one
+    sub-block, the sequence-parallel shapes 4444 / 8888) == attention over the concatenated keys.  Shards live in
+    separate buffers with more rows than used (kv_rows > nkv)."""
+    torch.manual_seed(7)
+    for (B, H, nq, lens) in [(1, 2, 300, (128, 128)), (1, 2, 200, (64, 200, 30)), (2, 3, 443, (443, 443)),
+                             (1, 2, 384, (1, 129, 65, 191)), (1, 2, 500, (4444, 4444, 4444, 4444)), (1, 1, 260, (8888, 8888))]:
+        nkv = sum(lens)
+        q = torch.randn(B, H, nq, 64, device=dev).bfloat16()
+        k = torch.randn(B, H, nkv, 64, device=dev).bfloat16()
+        v = torch.randn(B, H, nkv, 64, device=dev).bfloat16()
+        shards, o = [], 0
+        for n in lens:
+            kb = torch.full((B, H, n + 37, 64), float("nan"), device=dev, dtype=torch.bfloat16)   # rows beyond nkv: poison
+            vb = torch.full((B, H, n + 37, 64), float("nan"), device=dev, dtype=torch.bfloat16)
+            kb[:, :, :n] = k[:, :, o:o + n]
+            vb[:, :, :n] = v[:, :, o:o + n]
+            shards.append((kb, vb, n))
+            o += n
+        lse = torch.zeros(B * H, nq, device=dev)
+        out = ops.attention_shards(q, shards, variant=variant, lse=lse)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+        report(f"attn shards v{variant} {lens}", out, ref.permute(0, 2, 1, 3).reshape(B, nq, H * 64))
+        s = (q.float() @ k.float().transpose(-1, -2)) * 0.125
+        report("   lse", lse, (torch.logsumexp(s, -1) * 1.4426950408889634).view(B * H, nq), LSE_TOL)
+        if variant == 0:   # bit-identical to the single-buffer launch when the shard boundaries fall on 128-key boxes
+            if all(n % 128 == 0 for n in lens[:-1]):
+                mono = ops.attention(q, k, v)
+                assert torch.equal(mono, out), f"shards {lens}: differs from the monolithic launch"
+
+
+def test_attention_shard_arrival_flags():
+    """A shard guarded by an arrival flag is not read before the flag reaches the expected value: the flag is raised by
+    a stream memory operation on a SECOND stream after a delay and a late fill of the buffer; without the in-kernel wait
+    the kernel would read the poison the buffer holds until then.  A flag that never arrives times out after ~2 s,
+    raises the status word and does not hang."""
+    import ctypes as C
+
+    from landiff_b200 import _C
+
+    torch.manual_seed(8)
+    B, H, nq, n0, n1 = 1, 2, 256, 192, 320
+    q = torch.randn(B, H, nq, 64, device=dev).bfloat16()
+    k = torch.randn(B, H, n0 + n1, 64, device=dev).bfloat16()
+    v = torch.randn(B, H, n0 + n1, 64, device=dev).bfloat16()
+    k0, v0 = k[:, :, :n0].contiguous(), v[:, :, :n0].contiguous()
+    k1 = torch.full((B, H, n1, 64), float("nan"), device=dev, dtype=torch.bfloat16)
+    v1 = torch.full((B, H, n1, 64), float("nan"), device=dev, dtype=torch.bfloat16)
+    flag = torch.zeros(64, device=dev, dtype=torch.int32)
+    side = torch.cuda.Stream()
+    # first use of a kernel triggers a lazy module load, which cannot proceed while another kernel of this context is
+    # spinning: run everything the side stream will launch once before (in production the spinning kernel waits for a
+    # PEER's copy engine, which needs nothing from this context)
+    with torch.cuda.stream(side):
+        torch.cuda._sleep(1000)
+        scratch = torch.empty_like(k1)
+        scratch.copy_(k[:, :, n0:])
+        _C.check(_C.load().ld_stream_write_u32(flag.data_ptr() + 128, 1, side.cuda_stream), "ld_stream_write_u32")
+    torch.cuda.synchronize()
+    out = ops.attention_shards(q, [(k0, v0, None), (k1, v1, None, flag.data_ptr(), 7)])   # starts, then spins on the flag
+    with torch.cuda.stream(side):
+        torch.cuda._sleep(int(2e7))                      # ~10 ms: the kernel is certainly waiting by now
+        k1.copy_(k[:, :, n0:])
+        v1.copy_(v[:, :, n0:])
+        _C.check(_C.load().ld_stream_write_u32(flag.data_ptr(), 7, side.cuda_stream), "ld_stream_write_u32")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    report("attn shard behind an arrival flag", out, ref.permute(0, 2, 1, 3).reshape(B, nq, H * 64))
+    assert ops.attention_status() == 0
+    # transfer ids wrap: (int32)(flag - value) >= 0
+    out = ops.attention_shards(q, [(k0, v0, None), (k1, v1, None, flag.data_ptr(), 5)])
+    torch.cuda.synchronize()
+    report("attn shard, flag already past the id", out, ref.permute(0, 2, 1, 3).reshape(B, nq, H * 64))
+    # a flag that never arrives: bounded wait, status bit, no hang
+    ops.attention_shards(q, [(k0, v0, None), (k1, v1, None, flag.data_ptr(), 9)])
+    torch.cuda.synchronize()
+    assert ops.attention_status() == 1 and ops.attention_status() == 0
 
 
 def test_row_kernels():
