@@ -444,37 +444,39 @@ __device__ __forceinline__ void attn_exact_body(const AttnShards& sh, const Attn
 // ------------------------------------------------------------------------------------------------------------
 // Fast path (round 2, "attn5").
 //
-// Two 128-row query tiles per CTA.  Each 32-row TMEM quadrant of a tile is served by a PAIR of warps that split the 64
-// columns of a sub-block (warp h exponentiates columns [32h, 32h+32)), which puts 4 warps with exponentials on every
-// SMSP.
+// Two 128-row query tiles per CTA, FOUR softmax streams: stream (t, b) exponentiates the 64-key sub-blocks i = b, b+2, ...
+// of query tile t; each of its 4 warps owns a 32-row TMEM quadrant and all 64 columns of the sub-block.  Every SMSP
+// thus holds one warp of each stream — four INDEPENDENT instruction streams, so while one waits for the tensor pipe
+// (PV then the next S) the other three keep the exponential units busy (tools/softmax_mix_bench.cu: >= 3 warps per
+// SMSP are needed to reach the MUFU limit), and a warp pays one barrier wait + one barrier arrive per 64 columns.
 //
 // What bounds the kernel is the exponential: 16 384 of them per 128x128 score tile at 16 / clk / SM on the MUFU unit
-// is 1024 clk against 512 clk of tensor work.  Round-2 changes, all aimed at that (tools/softmax_mix_bench.cu,
-// profiles/r2_softmax_mix_bench.txt: 8.1 -> 6.0 clk per warp-element with 4 warps per SMSP):
+// is 1024 clk against 512 clk of tensor work.  Round-2 changes, all aimed at that (profiles/r2_softmax_mix_bench.txt:
+// 8.1 -> 6.0 clk per warp-element with 4 warps per SMSP):
 //   * the row sum is no longer an FADD per element: the tensor core accumulates it, L_t += P(t,i) x ones (an N = 16 MMA
 //     against a constant tile, 12 clk), from exactly the bf16 P values the PV product uses;
 //   * the scale-subtract is a packed FFMA2 per column pair;
 //   * KP of every 16 column pairs are exponentiated by a packed f32x2 polynomial on the FMA pipe (ex2_poly_pair), the
 //     rest by MUFU.EX2;
-//   * the score buffer is handed back to the tensor pipe as soon as the softmax warps have LOADED it (s_free), not when
-//     they have finished with it: S(t,i+1) is computed while the exponentials of S(t,i) run, so one score buffer per tile
-//     suffices and the softmax never waits for the tensor pipe; P has two buffers per tile, so it never waits for PV.
+//   * no running maximum, hence no rescaling, hence the two streams of a tile accumulate into ONE output accumulator
+//     O_t and ONE row-sum accumulator L_t (a sum is a sum), and there is nothing to merge in the epilogue.
 //
 // Reference maximum: floating point is scale-invariant, so the online-softmax reference only has to prevent overflow,
 // not track the running maximum.  Each row takes the maximum of its FIRST sub-block as the reference for the whole row
-// (both warps of a pair load that sub-block entirely, so they agree without communicating) and never rescales: later
-// scores may exceed the reference by up to 2^127 before exp2 overflows, and terms far below it flush to zero exactly
-// as their true weight demands.  Overflow (a score more than ~127 log2-units above the first block's maximum — never
-// seen on LayerNormed q/k, but constructible) makes the row sum or the output non-finite; the CTA then re-runs its
-// 256 rows through the exact path above in the same launch.  tests/test_kernels_gpu.py::test_attention_overflow_fixup.
+// (stream (t,0) computes it and hands it to stream (t,1) through shared memory) and never rescales: later scores may
+// exceed the reference by up to 2^127 before exp2 overflows, and terms far below it flush to zero exactly as their
+// true weight demands.  Overflow (a score more than ~127 log2-units above the first block's maximum — never seen on
+// LayerNormed q/k, but constructible) makes the row sum or the output non-finite; the CTA then re-runs its 256 rows
+// through the exact path above in the same launch.  tests/test_kernels_gpu.py::test_attention_overflow_fixup.
 //
 // Q is stored once into TMEM (bf16 pairs, one row per lane) by the softmax threads, so S = Q K^T runs as a TS-mode MMA
-// whose only shared-memory operand is the K sub-block: 32 clk per 128x64x16 instead of 48 (tools/mma_bench.cu).
-//   warps 0-15: softmax (tile w>>3, column half (w>>2)&1, TMEM quadrant w&3)   16: builds the sub-block table
-//   17: TMA producer   18, 19: MMA issuers of query tile 0 and 1 (independent instruction streams; K/V ring stages are
-//   released by one commit from each).
-//   TMEM columns: S_t at 64t [0,128) ; P(t,b) at 128+64t+32b [128,256) ; O_t at 256+64t [256,384) ;
-//                 Q_t at 384+32t [384,448) ; L_t (row sums, 16 identical columns) at 448+16t [448,480)
+// whose only shared-memory operand is the K sub-block: 32 clk per 128x64x16 instead of 48 (tools/mma_bench.cu).  P is
+// written in place over the first 32 columns of the stream's score buffer (only the writing warp ever reads those).
+//   warps 0-15: softmax (stream w>>2 = 2t+b, TMEM quadrant w&3)   16: builds the sub-block table   17: TMA producer
+//   18, 19: MMA issuers of query tile 0 and 1 (independent instruction streams; K/V ring stages are released by one
+//   commit from each).
+//   TMEM columns: S/P(t,b) at 64(2t+b) [0,256) ; O_t at 256+64t [256,384) ; Q_t at 384+32t [384,448) ;
+//                 L_t (row sums, 16 identical columns) at 448+16t [448,480)
 template <int KP, bool TRUNC, bool PROF>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
@@ -484,17 +486,16 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
   uint8_t* sV = smem + kOffV;
   uint32_t* sOnes = reinterpret_cast<uint32_t*>(smem + kOffOnes);
   uint32_t* tab = reinterpret_cast<uint32_t*>(smem + kOffTab);
+  float* sRef = reinterpret_cast<float*>(smem + kOffML);   // [tile][128] reference maximum * scale_log2
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBarsFast);
   uint64_t* q_ready = bars;              // [tile] = 2
   uint64_t* k_full = bars + 2;           // kKS
   uint64_t* k_empty = k_full + kKS;
   uint64_t* v_full = k_empty + kKS;
   uint64_t* v_empty = v_full + kKS;
-  uint64_t* s_full = v_empty + kKS;      // [t] = 2   S(t,i) is in TMEM
-  uint64_t* s_free = s_full + 2;         // [t] = 2   the 8 softmax warps of tile t hold S(t,i) in registers
-  uint64_t* p_full = s_free + 2;         // [t][b] = 4  P(t,i) is in TMEM
-  uint64_t* p_free = p_full + 4;         // [t][b] = 4  PV(t,i) has consumed P buffer b
-  uint64_t* all_done = p_free + 4;       // 1: every MMA of this CTA has completed
+  uint64_t* s_full = v_empty + kKS;      // [stream] = 4   S(t,i) is in TMEM
+  uint64_t* p_full = s_full + 4;         // [stream] = 4   P(t,i) is in TMEM
+  uint64_t* all_done = p_full + 4;       // 1: every MMA of this CTA has completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffSlot);
 
   const int warp = threadIdx.x >> 5;
@@ -516,14 +517,10 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 2);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_ready[i], 128);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 8);
-    }
+    for (int i = 0; i < 2; ++i) mbar_init(&q_ready[i], 128);
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&p_full[i], 8);
-      mbar_init(&p_free[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
     }
     mbar_init(all_done, 2);
     fence_barrier_init();
@@ -556,45 +553,42 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
       const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK));
       const uint64_t vdesc = make_sdesc_sw128(smem_u32(sV));
       const uint64_t odesc = make_sdesc_sw128(smem_u32(sOnes));
-      const uint32_t tm_s = tmem_base + 64 * t;
-      const uint32_t tm_p = tmem_base + 128 + 64 * t;   // P(t,0); P(t,1) 32 columns further
+      const uint32_t tm_s = tmem_base + 128 * t;        // S/P(t,0); S/P(t,1) 64 columns further
       const uint32_t tm_o = tmem_base + 256 + 64 * t;
       const uint32_t tm_q = tmem_base + 384 + 32 * t;
       const uint32_t tm_l = tmem_base + 448 + 16 * t;
-      long long w_k = 0, w_v = 0, w_p = 0, w_s = 0, i_s = 0, i_pv = 0, t_all = 0;
+      long long w_k = 0, w_v = 0, w_p = 0, i_s = 0, i_pv = 0, t_all = 0;
+      const uint32_t tab_s = smem_u32(tab);
+      auto tab_at = [&](int i) {   // explicit ld.shared (the generic pointer would compile to a generic LD)
+        uint32_t e;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(tab_s + 4u * uint32_t(i)));
+        return e;
+      };
       // descriptor address units are 16 B: ring stage = 1024, 64-row half = 512
-      // S(t, i) = Q_t K_i^T ; Q_t from TMEM (8 columns per 16-dim K step)
-      auto s_step = [&](int i) {
-        const uint32_t e = tab[i];
+      // S(t, i) = Q_t K_i^T into the buffer of stream (t, i&1); Q_t from TMEM (8 columns per 16-dim K step)
+      auto k_wait = [&](uint32_t e) {
+        if (tab_half(e) == 0) mbar_wait(&k_full[tab_box(e) % kKS], (tab_box(e) / kKS) & 1);
+      };
+      auto v_wait = [&](uint32_t e) {
+        if (tab_half(e) == 0) mbar_wait(&v_full[tab_box(e) % kKS], (tab_box(e) / kKS) & 1);
+      };
+      auto issue_s = [&](int i, uint32_t e) {
         const int st = tab_box(e) % kKS;
-        long long c0 = 0;
-        if constexpr (PROF) c0 = clock64();
-        if (tab_half(e) == 0) mbar_wait(&k_full[st], (tab_box(e) / kKS) & 1);
-        if constexpr (PROF) { const long long c1 = clock64(); w_k += c1 - c0; c0 = c1; }
-        tc_fence_after();
         const uint64_t bdesc = kdesc + uint32_t(st * (kTileBytes >> 4) + tab_half(e) * (kTileBytes >> 5));
+        const uint32_t d = tm_s + (i & 1) * 64;
         if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_ts(tm_s, tm_q + 8 * k, bdesc + 2 * k, idesc_s, k != 0);
-          umma_commit(&s_full[t]);
+          for (int k = 0; k < 4; ++k) umma_ts(d, tm_q + 8 * k, bdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[2 * t + (i & 1)]);
           if (tab_last(e)) umma_commit(&k_empty[st]);
         }
-        if constexpr (PROF) { __syncwarp(); i_s += clock64() - c0; }
       };
-      // O_t += P(t,i) V_i and L_t += P(t,i) 1 ; P: 128 lanes x 64 keys bf16 = 32 columns; 16 keys (8 columns) per MMA
-      auto pv_step = [&](int i) {
-        const uint32_t e = tab[i];
+      // O_t += P(t,i) V_i and L_t += P(t,i) 1 ; P: 128 lanes x 64 keys bf16 = the first 32 columns of the stream's score
+      // buffer; 16 keys (8 columns) per MMA
+      auto issue_pv = [&](int i, uint32_t e) {
         const int st = tab_box(e) % kKS;
-        const int b = i & 1;
-        long long c0 = 0;
-        if constexpr (PROF) c0 = clock64();
-        if (tab_half(e) == 0) mbar_wait(&v_full[st], (tab_box(e) / kKS) & 1);
-        if constexpr (PROF) { const long long c1 = clock64(); w_v += c1 - c0; c0 = c1; }
-        mbar_wait(&p_full[2 * t + b], (i >> 1) & 1);
-        if constexpr (PROF) { const long long c1 = clock64(); w_p += c1 - c0; c0 = c1; }
-        tc_fence_after();
         const uint64_t bdesc = vdesc + uint32_t(st * (kTileBytes >> 4) + tab_half(e) * (kTileBytes >> 5));
-        const uint32_t a = tm_p + 32 * b;
+        const uint32_t a = tm_s + (i & 1) * 64;
         if (leader) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -602,46 +596,65 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
             umma_ts(tm_o, a + 8 * k, bdesc + 128 * k, idesc_o, (i | k) != 0);
             umma_ts(tm_l, a + 8 * k, odesc, idesc_l, (i | k) != 0);
           }
-          umma_commit(&p_free[2 * t + b]);
           if (tab_last(e)) umma_commit(&v_empty[st]);
         }
-        if constexpr (PROF) { __syncwarp(); i_pv += clock64() - c0; }
       };
       mbar_wait(&q_ready[t], 0);
       if constexpr (PROF) t_all = clock64();
-      s_step(0);
+      uint32_t e_pv = tab_at(0);                          // sub-block i (PV side)
+      uint32_t e_s = n_sub > 1 ? tab_at(1) : 0u;          // sub-block i + 1, then i + 2 (S side)
+      k_wait(e_pv);
+      tc_fence_after();
+      issue_s(0, e_pv);
+      if (n_sub > 1) {
+        k_wait(e_s);
+        tc_fence_after();
+        issue_s(1, e_s);
+      }
       for (int i = 0; i < n_sub; ++i) {
-        if (i + 1 < n_sub) {
-          long long c0 = 0;
-          if constexpr (PROF) c0 = clock64();
-          mbar_wait(&s_free[t], i & 1);      // the softmax warps hold S(t,i) in registers: the buffer may be rewritten
-          if constexpr (PROF) w_s += clock64() - c0;
-          s_step(i + 1);
-        }
-        pv_step(i);
+        const bool has_next = i + 2 < n_sub;
+        const uint32_t e_n = has_next ? tab_at(i + 2) : 0u;
+        // The K / V stages needed by this iteration landed long ago (the rings run four boxes ahead), but even a
+        // completed mbarrier wait costs ~100 clk of latency in this serial chain: take those waits BEFORE the wait for
+        // the softmax (P(t,i)), where they overlap with time spent waiting anyway.
+        long long c0 = 0;
+        if constexpr (PROF) c0 = clock64();
+        v_wait(e_pv);
+        if constexpr (PROF) { const long long c1 = clock64(); w_v += c1 - c0; c0 = c1; }
+        if (has_next) k_wait(e_n);
+        if constexpr (PROF) { const long long c1 = clock64(); w_k += c1 - c0; c0 = c1; }
+        mbar_wait(&p_full[2 * t + (i & 1)], (i >> 1) & 1);
+        if constexpr (PROF) { const long long c1 = clock64(); w_p += c1 - c0; c0 = c1; }
+        tc_fence_after();
+        issue_pv(i, e_pv);
+        if constexpr (PROF) { __syncwarp(); const long long c1 = clock64(); i_pv += c1 - c0; c0 = c1; }
+        if (has_next) issue_s(i + 2, e_n);   // same buffer as P(t,i): the tensor pipe executes in issue order
+        if constexpr (PROF) { __syncwarp(); i_s += clock64() - c0; }
+        e_pv = e_s;
+        e_s = e_n;
       }
       if (leader) umma_commit(all_done);
       if constexpr (PROF) {
         if (leader && p.prof != nullptr) {
           long long* d = p.prof + ((int64_t)blockIdx.x * 20 + warp) * 8;
-          d[0] = w_k; d[1] = w_v; d[2] = w_p; d[3] = w_s; d[4] = i_s; d[5] = i_pv; d[6] = clock64() - t_all;
+          d[0] = w_k; d[1] = w_v; d[2] = w_p; d[3] = 0; d[4] = i_s; d[5] = i_pv; d[6] = clock64() - t_all;
         }
       }
     } else if (warp < 16) {
       reg_alloc<104>();   // 16 warps x 32 x 8 = 4096 <= the 5120 registers released by the control warpgroup
       // -------------------------------------------------------------------- softmax / epilogue
-      const int t = warp >> 3;                    // query tile
-      const int h = (warp >> 2) & 1;              // column half of every sub-block exponentiated by this warp
+      const int st = warp >> 2;                   // stream
+      const int t = st >> 1;                      // query tile
+      const int b = st & 1;                       // sub-block parity served by this stream
       const int quad = warp & 3;
       const int row_in_tile = quad * 32 + lane;
       const int q_row = q0 + t * 128 + row_in_tile;
       const uint32_t lane_base = uint32_t(quad * 32) << 16;
-      const uint32_t ts = tmem_base + lane_base + t * 64;                   // S_t
-      const uint32_t tpp = tmem_base + lane_base + 128 + t * 64 + 16 * h;   // this warp's 16 columns of P(t,0)
-      const uint32_t to = tmem_base + lane_base + 256 + t * 64;             // O_t
+      const uint32_t ts = tmem_base + lane_base + st * 64;         // S / P of this stream
+      const uint32_t to = tmem_base + lane_base + 256 + t * 64;    // O_t
       const float sl2 = p.scale_log2;
 
-      if (h == 0) {
+      if (b == 0) {
         // Q row -> TMEM (bf16 pairs: column c holds dims 2c, 2c+1), zero beyond nq
         uint32_t qr[32];
         if (q_row < p.nq) {
@@ -665,46 +678,44 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
       long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
       long long tp = 0;
       if constexpr (PROF) tp = clock64();
-      bool s_ready = false;   // s_full(i) already observed complete by the probe of the previous iteration
-      for (int i = 0; i < n_sub; ++i) {
-        const int b = i & 1;
-        if (!s_ready) mbar_wait(&s_full[t], i & 1);
+      int kk = 0;
+      for (int i = b; i < n_sub; i += 2, ++kk) {
+        mbar_wait(&s_full[st], kk & 1);
         tc_fence_after();
         LD_PROF(0);
-        uint32_t s[32];   // this warp's column half
-        LD_TMEM_LD32(ts + 32 * h, s);
-        const int valid = tab_valid(tab[i]) - 32 * h;
-        if (i == 0) {
-          // reference maximum of the row = maximum of the whole first sub-block (identical in both warps of the pair)
-          uint32_t so[32];
-          LD_TMEM_LD32(ts + 32 * (h ^ 1), so);
-          tmem_ld_wait();
-          const int valid_o = tab_valid(tab[0]) - 32 * (h ^ 1);
-          float mx = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            if (c < valid) mx = fmaxf(mx, __uint_as_float(s[c]));
-            if (c < valid_o) mx = fmaxf(mx, __uint_as_float(so[c]));
-          }
-          msc = mx * sl2;
-        } else {
-          tmem_ld_wait();
-        }
-        // S(t,i) is in registers: hand the score buffer back to the tensor pipe (S(t,i+1) runs under the exponentials)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[t]);
+        uint32_t s[64];
+        LD_TMEM_LD32(ts, s);
+        LD_TMEM_LD32(ts + 32, (s + 32));
+        tmem_ld_wait();
         LD_PROF(1);
-        if (valid < 32) {
+        const int valid = tab_valid(tab[i]);
+        if (valid < 64) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
+          for (int c = 0; c < 64; ++c)
             if (c >= valid) s[c] = 0xff800000u;  // -inf
         }
+        if (kk == 0) {
+          // one reference per ROW for both streams of the tile (they share O_t and L_t): the maximum of sub-block 0
+          if (b == 0) {
+            float mx4[4] = {__uint_as_float(s[0]), __uint_as_float(s[1]), __uint_as_float(s[2]), __uint_as_float(s[3])};
+#pragma unroll
+            for (int c = 4; c < 64; c += 4) {
+              mx4[0] = fmaxf(mx4[0], __uint_as_float(s[c]));
+              mx4[1] = fmaxf(mx4[1], __uint_as_float(s[c + 1]));
+              mx4[2] = fmaxf(mx4[2], __uint_as_float(s[c + 2]));
+              mx4[3] = fmaxf(mx4[3], __uint_as_float(s[c + 3]));
+            }
+            msc = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sl2;
+            sRef[t * 128 + row_in_tile] = msc;
+          }
+          named_bar_sync(1 + t * 4 + quad, 64);   // the two warps (b = 0, 1) that own these 32 rows
+          if (b == 1) msc = sRef[t * 128 + row_in_tile];
+        }
         LD_PROF(2);
-        uint32_t pk[16];
+        uint32_t pk[32];
         const uint64_t sc2 = pack2(sl2, sl2), nm2 = pack2(-msc, -msc);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < 32; ++c) {
           const uint64_t x2 = fma2(pack2u(s[2 * c], s[2 * c + 1]), sc2, nm2);
           float p0, p1;
           if (KP > 0 && ((c * KP) % 16) < KP) {   // KP of 16 pairs, evenly spread, on the FMA pipe
@@ -724,21 +735,15 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
           }
         }
         LD_PROF(3);
-        // probe the barrier the next iteration starts with (almost always complete: S(t,i+1) was issued at s_free(i))
-        s_ready = (i + 1 < n_sub) && mbar_test_wait(&s_full[t], (i + 1) & 1);
-        if (i >= 2) {
-          mbar_wait(&p_free[2 * t + b], ((i >> 1) - 1) & 1);   // PV(t,i-2) has consumed this P buffer (long ago)
-          tc_fence_after();
-        }
-        LD_TMEM_ST16(tpp + 32 * b, pk);
+        LD_TMEM_ST32(ts, pk);
         tmem_st_wait();
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[2 * t + b]);
+        mbar_arrive(&p_full[st]);
         LD_PROF(4);
       }
+      if (n_sub == 1 && b == 1) named_bar_sync(1 + t * 4 + quad, 64);   // pair barrier of a stream without any sub-block
 
-      // ---- epilogue: the row sum comes from the tensor core (L_t); warp h writes output columns [32h, 32h+32)
+      // ---- epilogue: the row sum comes from the tensor core (L_t); stream b writes output columns [32b, 32b+32)
       mbar_wait(all_done, 0);
       tc_fence_after();
       if constexpr (PROF) {
@@ -747,9 +752,10 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
           for (int e = 0; e < 6; ++e) d[e] = prof_acc[e];
         }
       }
+      if (b == 1) msc = sRef[t * 128 + row_in_tile];
       uint32_t lbits;
       LD_TMEM_LD1(tmem_base + lane_base + 448 + 16 * t, lbits);
-      const int c0 = 32 * h;
+      const int c0 = 32 * b;
       uint32_t o[32];
       LD_TMEM_LD32(to + c0, o);
       tmem_ld_wait();
@@ -780,7 +786,7 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
         }
         // truncated P values are low by 2^-9 on average (uniform mantissa tails): the normalisation above uses the same
         // values and needs no correction, the exported log-sum-exp does
-        if (h == 0 && p.lse != nullptr)
+        if (b == 0 && p.lse != nullptr)
           p.lse[(int64_t)bh * p.nq + q_row] = msc + log2f(TRUNC ? l_all * 1.001953125f : l_all);
       }
     }

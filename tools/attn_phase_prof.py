@@ -28,11 +28,11 @@ ops.attention(q, k, v, out=out, variant=VAR)
 torch.cuda.synchronize()
 lib.ld_debug_attn_prof(None)
 n_sub = (N + 63) // 64
-per_warp = n_sub if VAR == 0 else n_sub / 2
+per_warp = n_sub / 2   # every softmax warp serves the sub-blocks of one parity
 p = prof.double().cpu()
 sm = p[:, FIRST:LAST, :5].mean(dim=(0, 1)) / per_warp
 names = ["wait s_full", "tcgen05.ld", "mask+max+rescale", "exp+sum+pack", "st+fence+arrive"]
-print(f"variant {VAR} N={N} n_sub={n_sub}: softmax warp cycles per 64-key sub-block it processes (mean over CTAs and warps)")
+print(f"variant {VAR} N={N} n_sub={n_sub}: softmax warp cycles per 64-key sub-block IT processes (each warp serves every other sub-block; mean over CTAs and warps)")
 for n, c in zip(names, sm.tolist()):
     print(f"  {n:20s} {c:8.1f}")
 print(f"  {'total':20s} {sm.sum().item():8.1f}")
