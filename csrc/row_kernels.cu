@@ -65,7 +65,106 @@ __device__ __forceinline__ void row_stats(const float (*vals)[8], int nvec, int 
   rstd = rsqrtf(warp_sum(q) / (float)D + eps);
 }
 
-// out = LN(x) * (1 + scale[seg]) + shift[seg]
+// out = LN(x) * (1 + scale[seg]) + shift[seg], rows streamed through shared memory by bulk async copies.
+//
+// The first version (ln_modulate_kernel below, kept for D that does not fit) held a whole row in registers: 124 registers,
+// 24 % occupancy, and every warp's load -> reduce -> store phases in series — 2.7 TB/s of the 6.5 TB/s a copy reaches
+// (profiles/r1_ncu_rows.csv).  Here each warp owns a 3-deep ring of row buffers filled by cp.async.bulk (one elected
+// lane, mbarrier complete_tx), so 3 rows per warp (184 KB per SM for fp32 rows) are in flight regardless of what the
+// warp is doing, and the row is read from shared memory three times (mean, variance, output) instead of living in
+// registers.  Quads of 4 elements per lane and step: 16-byte (fp32) / 8-byte (bf16) conflict-free shared-memory reads,
+// 8-byte coalesced stores.
+constexpr int kLnStages = 3;
+constexpr int kLnWarps = 8;
+
+template <typename TX>
+__device__ __forceinline__ float4 ld_quad(const TX* row, int q);
+template <>
+__device__ __forceinline__ float4 ld_quad<float>(const float* row, int q) {
+  return reinterpret_cast<const float4*>(row)[q];
+}
+template <>
+__device__ __forceinline__ float4 ld_quad<bf16>(const bf16* row, int q) {
+  const uint2 v = reinterpret_cast<const uint2*>(row)[q];
+  return make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+}
+
+template <typename TX>
+__global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_bulk_kernel(
+    const TX* __restrict__ x, bf16* __restrict__ out, const bf16* __restrict__ w, const bf16* __restrict__ b, float eps,
+    const float* __restrict__ shift_img, const float* __restrict__ scale_img, const float* __restrict__ shift_txt,
+    const float* __restrict__ scale_txt, int64_t mod_stride, int rows, int rows_per_batch, int tok_offset, int text_len,
+    int D) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t row_bytes = (uint32_t)D * sizeof(TX);
+  uint8_t* ring = ln_smem + (size_t)warp * kLnStages * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)kLnWarps * kLnStages * row_bytes) + warp * kLnStages;
+  const int nquad = D >> 2;
+  const int first = blockIdx.x * kLnWarps + warp;
+  const int stride = gridDim.x * kLnWarps;
+  if (lane == 0) {
+    for (int s = 0; s < kLnStages; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+    for (int s = 0; s < kLnStages; ++s) {
+      const int64_t r = (int64_t)first + (int64_t)s * stride;
+      if (r < rows) {
+        mbar_expect_tx(&bars[s], row_bytes);
+        bulk_load_1d(ring + s * row_bytes, x + r * D, row_bytes, &bars[s]);
+      }
+    }
+  }
+  __syncwarp();
+  const float inv_d = 1.0f / (float)D;
+  int it = 0;
+  for (int64_t row = first; row < rows; row += stride, ++it) {
+    const int s = it % kLnStages;
+    mbar_wait(&bars[s], (it / kLnStages) & 1);
+    const TX* xr = reinterpret_cast<const TX*>(ring + s * row_bytes);
+    float sum = 0.f;
+    for (int q = lane; q < nquad; q += 32) {
+      const float4 v = ld_quad<TX>(xr, q);
+      sum += (v.x + v.y) + (v.z + v.w);
+    }
+    const float mean = warp_sum(sum) * inv_d;
+    float sq = 0.f;
+    for (int q = lane; q < nquad; q += 32) {
+      const float4 v = ld_quad<TX>(xr, q);
+      const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+      sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
+    const int bidx = (int)(row / rows_per_batch);
+    const int t = (int)(row - (int64_t)bidx * rows_per_batch);
+    const bool is_text = (tok_offset + t) < text_len;
+    const float4* shift = reinterpret_cast<const float4*>((is_text ? shift_txt : shift_img) + (int64_t)bidx * mod_stride);
+    const float4* scale = reinterpret_cast<const float4*>((is_text ? scale_txt : scale_img) + (int64_t)bidx * mod_stride);
+    uint2* orow = reinterpret_cast<uint2*>(out + row * D);
+    for (int q = lane; q < nquad; q += 32) {
+      const float4 v = ld_quad<TX>(xr, q);
+      const uint2 wq = __ldg(reinterpret_cast<const uint2*>(w) + q), bq = __ldg(reinterpret_cast<const uint2*>(b) + q);
+      const float4 sc = __ldg(scale + q), sh = __ldg(shift + q);
+      const float y0 = fmaf((v.x - mean) * rstd, bf16_lo(wq.x), bf16_lo(bq.x));
+      const float y1 = fmaf((v.y - mean) * rstd, bf16_hi(wq.x), bf16_hi(bq.x));
+      const float y2 = fmaf((v.z - mean) * rstd, bf16_lo(wq.y), bf16_lo(bq.y));
+      const float y3 = fmaf((v.w - mean) * rstd, bf16_hi(wq.y), bf16_hi(bq.y));
+      uint2 o;
+      o.x = pack_bf16x2(fmaf(y0, 1.0f + sc.x, sh.x), fmaf(y1, 1.0f + sc.y, sh.y));
+      o.y = pack_bf16x2(fmaf(y2, 1.0f + sc.z, sh.z), fmaf(y3, 1.0f + sc.w, sh.w));
+      orow[q] = o;
+    }
+    __syncwarp();   // every lane has finished reading this stage
+    const int64_t nxt = row + (int64_t)kLnStages * stride;
+    if (lane == 0 && nxt < rows) {
+      fence_proxy_async_smem();   // generic-proxy reads of the stage are ordered before the async-proxy refill
+      mbar_expect_tx(&bars[s], row_bytes);
+      bulk_load_1d(ring + s * row_bytes, x + nxt * D, row_bytes, &bars[s]);
+    }
+  }
+}
+
+// out = LN(x) * (1 + scale[seg]) + shift[seg]   (register-resident row; fallback for rows the bulk version cannot take)
 template <typename TX>
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const TX* __restrict__ x, bf16* __restrict__ out,
                                                           const bf16* __restrict__ w, const bf16* __restrict__ b,
@@ -257,6 +356,55 @@ __global__ void __launch_bounds__(256) small_linear_kernel(const float* __restri
   }
 }
 
+// The same GEMV for L independent weight matrices in ONE launch (blockIdx.y = matrix): all adaLN modulation projections of a
+// network share their input (the time embedding), dit_video_concat.py:555 evaluates them layer by layer.
+template <int MAXB>
+__global__ void __launch_bounds__(256) small_linear_batched_kernel(const float* __restrict__ x, const bf16* const* __restrict__ Ws,
+                                                                   const bf16* const* __restrict__ biases,
+                                                                   float* __restrict__ y, int batch, int N, int K, int act_in,
+                                                                   int round_bf16) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int l = blockIdx.y;
+  const bf16* W = Ws[l];
+  const bf16* bias = biases[l];
+  float acc[MAXB];
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) acc[b] = 0.f;
+  const uint4* wr = reinterpret_cast<const uint4*>(W + (int64_t)n * K);
+  for (int v = lane; v < (K >> 3); v += 32) {
+    float wv[8];
+    unpack8(wr[v], wv);
+#pragma unroll
+    for (int b = 0; b < MAXB; ++b)
+      if (b < batch) {
+        const float4 x0 = reinterpret_cast<const float4*>(x + (int64_t)b * K)[2 * v];
+        const float4 x1 = reinterpret_cast<const float4*>(x + (int64_t)b * K)[2 * v + 1];
+        float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float xi = xv[j];
+          if (act_in == 1) {
+            xi = silu(xi);
+            if (round_bf16) xi = __bfloat162float(__float2bfloat16_rn(xi));
+          }
+          acc[b] = fmaf(xi, wv[j], acc[b]);
+        }
+      }
+  }
+#pragma unroll
+  for (int b = 0; b < MAXB; ++b) acc[b] = warp_sum(acc[b]);
+  if (lane == 0) {
+    const float bv = bias ? __bfloat162float(bias[n]) : 0.f;
+    for (int b = 0; b < batch; ++b) {
+      float v = acc[b] + bv;
+      if (round_bf16) v = __bfloat162float(__float2bfloat16_rn(v));
+      y[((int64_t)l * batch + b) * N + n] = v;
+    }
+  }
+}
+
 // [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(max_period) i / half)   (sgm/.../util.py:207-233)
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int batch, int dim,
                                           float max_period, int round_bf16) {
@@ -325,17 +473,51 @@ extern "C" int ld_layernorm_modulate(const void* x, int x_is_f32, void* out, con
   LD_CHECK_ARG(D % 8 == 0 && D > 0 && D <= 2048, "ld_layernorm_modulate: D=%d must be a multiple of 8 and <= 2048", D);
   LD_CHECK_ARG(batch > 0 && rows_per_batch > 0, "ld_layernorm_modulate: empty input");
   const int rows = batch * rows_per_batch;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t esz = x_is_f32 ? 4 : 2;
+  const size_t smem = (size_t)kLnWarps * kLnStages * D * esz + kLnWarps * kLnStages * 8;
+  // the bulk-copy version needs 16-byte row granularity and its ring in shared memory; mod vectors must be 16-byte aligned
+  const bool aligned = ((D * esz) % 16 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (mod_batch_stride % 4 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(shift_img) | reinterpret_cast<uintptr_t>(scale_img) |
+                         reinterpret_cast<uintptr_t>(shift_txt) | reinterpret_cast<uintptr_t>(scale_txt)) % 16 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) % 8 == 0);
+  if (aligned && smem <= 200 * 1024) {
+    static bool attr_set[64][2] = {};
+    int dev = 0;
+    LD_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev][x_is_f32 ? 1 : 0]) {
+      if (x_is_f32)
+        LD_CHECK_CUDA(cudaFuncSetAttribute(ln_modulate_bulk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      else
+        LD_CHECK_CUDA(cudaFuncSetAttribute(ln_modulate_bulk_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set[dev][x_is_f32 ? 1 : 0] = true;
+    }
+    const int blocks_per_sm = smem <= 100 * 1024 ? 2 : 1;
+    const int grid = grid_for(rows, kLnWarps, sm_count() * blocks_per_sm);
+    if (x_is_f32)
+      ln_modulate_bulk_kernel<float><<<grid, kLnWarps * 32, smem, st>>>((const float*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
+                                                                         eps, shift_img, scale_img, shift_txt, scale_txt,
+                                                                         mod_batch_stride, rows, rows_per_batch, tok_offset,
+                                                                         text_len, D);
+    else
+      ln_modulate_bulk_kernel<bf16><<<grid, kLnWarps * 32, smem, st>>>((const bf16*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
+                                                                        eps, shift_img, scale_img, shift_txt, scale_txt,
+                                                                        mod_batch_stride, rows, rows_per_batch, tok_offset,
+                                                                        text_len, D);
+    LD_CHECK_CUDA(cudaGetLastError());
+    return LD_OK;
+  }
   const int grid = grid_for(rows, 8, sm_count() * 16);
   if (x_is_f32)
-    ln_modulate_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
-                                                                       eps, shift_img, scale_img, shift_txt, scale_txt,
-                                                                       mod_batch_stride, rows, rows_per_batch, tok_offset,
-                                                                       text_len, D);
+    ln_modulate_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
+                                                    eps, shift_img, scale_img, shift_txt, scale_txt,
+                                                    mod_batch_stride, rows, rows_per_batch, tok_offset,
+                                                    text_len, D);
   else
-    ln_modulate_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
-                                                                      eps, shift_img, scale_img, shift_txt, scale_txt,
-                                                                      mod_batch_stride, rows, rows_per_batch, tok_offset,
-                                                                      text_len, D);
+    ln_modulate_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
+                                                   eps, shift_img, scale_img, shift_txt, scale_txt,
+                                                   mod_batch_stride, rows, rows_per_batch, tok_offset,
+                                                   text_len, D);
   LD_CHECK_CUDA(cudaGetLastError());
   return LD_OK;
 }
@@ -402,6 +584,25 @@ extern "C" int ld_small_linear(const float* x, const void* W, const void* bias, 
     small_linear_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)W, (const bf16*)bias, y, batch, N, K, act_in, act_out, round_bf16);
   else
     small_linear_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const bf16*)W, (const bf16*)bias, y, batch, N, K, act_in, act_out, round_bf16);
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}
+
+extern "C" int ld_small_linear_batched(const float* x, const void* const* Ws, const void* const* biases, float* y, int layers,
+                                       int batch, int N, int K, int act_in, int round_bf16, void* stream) {
+  int rc = check_device();
+  if (rc != LD_OK) return rc;
+  LD_CHECK_ARG(x && Ws && biases && y, "ld_small_linear_batched: null pointer");
+  LD_CHECK_ARG(layers >= 1 && layers <= 65535, "ld_small_linear_batched: layers=%d out of range", layers);
+  LD_CHECK_ARG(batch >= 1 && batch <= 8, "ld_small_linear_batched: batch=%d must be in [1,8]", batch);
+  LD_CHECK_ARG(K % 8 == 0 && N > 0, "ld_small_linear_batched: K=%d must be a multiple of 8", K);
+  const dim3 grid((N + 7) / 8, layers);
+  if (batch <= 2)
+    small_linear_batched_kernel<2><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const bf16* const*)Ws, (const bf16* const*)biases, y,
+                                                                           batch, N, K, act_in, round_bf16);
+  else
+    small_linear_batched_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (const bf16* const*)Ws, (const bf16* const*)biases, y,
+                                                                           batch, N, K, act_in, round_bf16);
   LD_CHECK_CUDA(cudaGetLastError());
   return LD_OK;
 }

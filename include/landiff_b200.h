@@ -158,6 +158,13 @@ int ld_patchify(const void* x, int x_is_f32, const void* sem, int sem_is_f32, vo
 int ld_small_linear(const float* x, const void* W, const void* bias, float* y, int batch, int N, int K, int act_in,
                     int act_out, int round_bf16, void* stream);
 
+/* the same GEMV for `layers` weight matrices of identical shape that share the input x, ONE launch:
+   y[l, b, n] = sum_k act_in(x[b,k]) * Ws[l][n,k] + biases[l][n].  Ws / biases: DEVICE arrays of `layers` device pointers
+   (biases[l] may be NULL).  All adaLN_modulation projections of a network in one pass (dit_video_concat.py:510-515/:555
+   evaluates them layer by layer from the same time embedding). */
+int ld_small_linear_batched(const float* x, const void* const* Ws, const void* const* biases, float* y, int layers, int batch,
+                            int N, int K, int act_in, int round_bf16, void* stream);
+
 /* sinusoidal timestep embedding, [cos | sin] (sgm/modules/diffusionmodules/util.py:207-233) -> fp32 [B, dim] */
 int ld_timestep_embedding(const float* t, float* out, int batch, int dim, float max_period, int round_bf16,
                           void* stream);

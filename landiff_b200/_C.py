@@ -66,6 +66,7 @@ SIGNATURES = {
     "ld_final_norm_modulate": (C.c_int, [_vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _f, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp]),
     "ld_patchify": (C.c_int, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ld_small_linear": (C.c_int, [_fp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ld_small_linear_batched": (C.c_int, [_fp, _vp, _vp, _fp, _i, _i, _i, _i, _i, _i, _vp]),
     "ld_timestep_embedding": (C.c_int, [_fp, _fp, _i, _i, _f, _i, _vp]),
     "ld_sampler_update": (C.c_int, [_fp, _vp, _vp, _fp, _fp, _fp, _fp, _i64] + [_f] * 8 + [_i, _i, _vp]),
 }
@@ -77,7 +78,7 @@ def lib_path() -> Path:
     return _build.LIB_PATH
 
 
-ABI_VERSION = 2   # must equal ld_abi_version() of the loaded library (bumped whenever a signature or struct changes)
+ABI_VERSION = 3   # must equal ld_abi_version() of the loaded library (bumped whenever a signature or struct changes)
 
 
 def load() -> C.CDLL:

@@ -340,9 +340,16 @@ class DiffusionTransformer(nn.Module):
         te = self.time_embed
         ops.small_linear(ws["temb"], te[0].weight, te[0].bias, act_out=1, out=ws["e1"])
         ops.small_linear(ws["e1"], te[2].weight, te[2].bias, out=ws["emb"])
+        # adaLN_modulation(emb) = Linear(SiLU(emb)) for every layer (:555-568): ONE batched GEMV over the layers' weight
+        # matrices (a device table of their addresses, rebuilt only if a parameter's storage moves)
         ada = self.mixins["adaln_layer"].adaLN_modulations
-        for i in range(self.num_layers):  # adaLN_modulation(emb) = Linear(SiLU(emb)) (:555-568)
-            ops.small_linear(ws["emb"], ada[i][1].weight, ada[i][1].bias, act_in=1, out=ws["mod"][i])
+        key = tuple(ada[i][1].weight.data_ptr() for i in range(self.num_layers))
+        if ws.get("ada_key") != key:
+            ws["ada_w"] = ops.pointer_table([ada[i][1].weight for i in range(self.num_layers)], ws["mod"].device)
+            ws["ada_b"] = ops.pointer_table([ada[i][1].bias for i in range(self.num_layers)], ws["mod"].device)
+            ws["ada_key"] = key
+        ops.small_linear_batched(ws["emb"], ws["ada_w"], ws["ada_b"], self.num_layers, 12 * self.hidden_size, act_in=1,
+                                 out=ws["mod"])
 
     def _embed(self, ws, x, context, sem):
         B, T, C, H, W = x.shape

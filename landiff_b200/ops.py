@@ -286,6 +286,30 @@ def small_linear(x, w, bias, act_in=0, act_out=0, round_bf16=True, out=None):
     return out
 
 
+def small_linear_batched(x, w_ptrs, b_ptrs, layers, N, act_in=0, round_bf16=True, out=None):
+    """y[l] = act_in(x) @ W_l.T + b_l for `layers` same-shaped bf16 matrices in one launch.  w_ptrs / b_ptrs: int64 CUDA
+    tensors holding the device addresses of the matrices / bias vectors (see `pointer_table`)."""
+    _chk(x, F32, "x")
+    Bn, K = x.shape
+    for nm, t_ in (("w_ptrs", w_ptrs), ("b_ptrs", b_ptrs)):
+        _chk(t_, torch.int64, nm)
+        if t_.numel() != layers:
+            raise ValueError(f"small_linear_batched: {nm} must hold {layers} pointers")
+    if out is None:
+        out = torch.empty((layers, Bn, N), dtype=F32, device=x.device)
+    _chk(out, F32, "out")
+    if out.numel() != layers * Bn * N:
+        raise ValueError("small_linear_batched: out must hold [layers, B, N]")
+    check(_C.load().ld_small_linear_batched(x.data_ptr(), w_ptrs.data_ptr(), b_ptrs.data_ptr(), out.data_ptr(), layers, Bn, N, K,
+                                            act_in, int(round_bf16), _stream()), "ld_small_linear_batched")
+    return out
+
+
+def pointer_table(tensors, device) -> torch.Tensor:
+    """int64 CUDA tensor of the device addresses of `tensors` (None -> 0)."""
+    return torch.tensor([0 if t is None else t.data_ptr() for t in tensors], dtype=torch.int64, device=device)
+
+
 def timestep_embedding(t, dim, max_period=10000.0, round_bf16=True, out=None):
     _chk(t, F32, "t")
     Bn = t.numel()
@@ -361,6 +385,7 @@ def register_torch_ops() -> None:
       "Tensor scale, int mod_batch_stride, int batch, int rows_per_batch, int tok_offset, int text_len) -> Tensor")
     D("patchify(Tensor x, Tensor? sem, int g0=0, int n=-1) -> Tensor")
     D("small_linear(Tensor x, Tensor w, Tensor? bias, int act_in=0, int act_out=0, bool round_bf16=True) -> Tensor")
+    D("small_linear_batched(Tensor x, Tensor[] ws, Tensor[] biases, int act_in=0, bool round_bf16=True) -> Tensor")
     D("timestep_embedding(Tensor t, int dim, float max_period=10000.0, bool round_bf16=True) -> Tensor")
     D("sampler_update(Tensor x, Tensor net_u, Tensor net_c, Tensor? old_den, Tensor? eps, float c_skip, "
       "float c_out, float cfg, float m1, float m2, float m3, float m4, float mn, int mode) -> (Tensor, Tensor)")
@@ -406,6 +431,10 @@ def register_torch_ops() -> None:
         gemm(a, w, epilogue=EPI_UNPATCHIFY, bias=bias, out=out, rows_per_batch=rows_per_batch, tok_offset=tok_offset,
              text_len=text_len, patch_grid=(T, Hp, Wp, C_))
 
+    def _small_linear_batched(x, ws, biases, act_in=0, round_bf16=True):
+        return small_linear_batched(x, pointer_table(ws, x.device), pointer_table(biases, x.device), len(ws), ws[0].shape[0],
+                                    act_in=act_in, round_bf16=round_bf16)
+
     def _patchify(x, sem, g0=0, n=-1):
         return patchify(x, sem, g0=g0, n=None if n < 0 else n)
 
@@ -417,7 +446,8 @@ def register_torch_ops() -> None:
                      ("linear", _linear), ("linear_gated_residual", _linear_gated_residual), ("linear_qkv", _linear_qkv),
                      ("linear_bias_pos", _linear_bias_pos), ("linear_unpatchify", _linear_unpatchify),
                      ("layernorm_modulate", layernorm_modulate), ("final_norm_modulate", final_norm_modulate),
-                     ("patchify", _patchify), ("small_linear", small_linear), ("timestep_embedding", timestep_embedding),
+                     ("patchify", _patchify), ("small_linear", small_linear), ("small_linear_batched", _small_linear_batched),
+                     ("timestep_embedding", timestep_embedding),
                      ("sampler_update", _sampler_update)):
         lib.impl(name, fn, "CUDA")
     register_torch_ops._lib = lib  # keep alive
@@ -426,6 +456,6 @@ def register_torch_ops() -> None:
 
 TORCH_OPS = ("attention", "attention_lse", "attention_merge", "linear", "linear_gated_residual", "linear_qkv",
              "linear_bias_pos", "linear_unpatchify", "layernorm_modulate", "final_norm_modulate", "patchify", "small_linear",
-             "timestep_embedding", "sampler_update")
+             "small_linear_batched", "timestep_embedding", "sampler_update")
 
 register_torch_ops()

@@ -11,7 +11,7 @@ NS = torch.ops.landiff_b200
 
 
 def test_every_compute_entry_point_is_a_registered_op():
-    assert len(ops.TORCH_OPS) == 14
+    assert len(ops.TORCH_OPS) == 15
     for name in ops.TORCH_OPS:
         op = getattr(NS, name)
         assert "landiff_b200::" + name in str(op.default._schema)
@@ -85,6 +85,13 @@ def test_ops_match_the_ctypes_path():
     xe = torch.randn(B, 64, device=dev)
     wl = (torch.randn(96, 64, device=dev) * 0.05).bfloat16()
     assert eq(NS.small_linear(xe, wl, None, 1, 0, True), ops.small_linear(xe, wl, None, act_in=1))
+    # batched GEMV (all adaLN projections of a network in one launch) == the per-layer launches, bit for bit
+    wls = [(torch.randn(96, 64, device=dev) * 0.05).bfloat16() for _ in range(5)]
+    bls = [(torch.randn(96, device=dev) * 0.1).bfloat16() for _ in range(5)]
+    yb = NS.small_linear_batched(xe, wls, bls, 1, True)
+    assert yb.shape == (5, B, 96)
+    for l in range(5):
+        assert eq(yb[l], ops.small_linear(xe, wls[l], bls[l], act_in=1)), l
     t = torch.tensor([999.0, 19.0], device=dev)
     assert eq(NS.timestep_embedding(t, 128), ops.timestep_embedding(t, 128))
     xl, old, eps = [torch.randn(1, 2, 4, 6, 8, device=dev) for _ in range(3)]

@@ -36,9 +36,9 @@ print(f"variant {VAR} N={N} n_sub={n_sub}: softmax warp cycles per 64-key sub-bl
 for n, c in zip(names, sm.tolist()):
     print(f"  {n:20s} {c:8.1f}")
 print(f"  {'total':20s} {sm.sum().item():8.1f}")
-for w in (18, 19):
+for w in (17, 18, 19):
     mm = p[:, w, :7].mean(dim=0) / n_sub
-    print("MMA issuer warp %d per sub-block: wait k_full %.1f  v_full %.1f  p_full %.1f  s_free %.1f | issue S %.1f  issue PV+L %.1f | loop total %.1f" % ((w,) + tuple(mm.tolist())))
+    print("issuer warp %d (17: scores of both tiles; 18/19: PV + row sums) per sub-block: wait k_full %.1f  v_full %.1f  p_full %.1f  s_free %.1f | issue S %.1f  issue PV+L %.1f | loop total %.1f" % ((w,) + tuple(mm.tolist())))
 # spread between the softmax warps of a CTA (the slowest of the 8 warps of a tile gates p_full / s_free)
 tot = p[:, FIRST:LAST, :5].sum(dim=2) / per_warp
 print("softmax loop cycles per sub-block by warp (mean over CTAs):", " ".join(f"{v:.0f}" for v in tot.mean(dim=0).tolist()))
