@@ -446,8 +446,9 @@ __device__ __forceinline__ void attn_exact_body(const AttnShards& sh, const Attn
 //
 // Two 128-row query tiles per CTA, FOUR softmax streams: stream (t, b) exponentiates the 64-key sub-blocks i = b, b+2, ...
 // of query tile t; each of its 4 warps owns a 32-row TMEM quadrant and all 64 columns of the sub-block.  Every SMSP
-// thus holds one warp of each stream — four INDEPENDENT instruction streams (tools/softmax_mix_bench.cu: >= 3 warps
-// per SMSP are needed to reach the MUFU limit), and a warp pays its barrier operations once per 64 columns.
+// thus holds one warp of each stream — four INDEPENDENT instruction streams, so while one waits for the tensor pipe
+// (PV then the next S) the other three keep the exponential units busy (tools/softmax_mix_bench.cu: >= 3 warps per
+// SMSP are needed to reach the MUFU limit), and a warp pays one barrier wait + one barrier arrive per 64 columns.
 //
 // What bounds the kernel is the exponential: 16 384 of them per 128x128 score tile at 16 / clk / SM on the MUFU unit
 // is 1024 clk against 512 clk of tensor work.  Round-2 changes, all aimed at that (profiles/r2_softmax_mix_bench.txt:
@@ -458,10 +459,7 @@ __device__ __forceinline__ void attn_exact_body(const AttnShards& sh, const Attn
 //   * KP of every 16 column pairs are exponentiated by a packed f32x2 polynomial on the FMA pipe (ex2_poly_pair), the
 //     rest by MUFU.EX2;
 //   * no running maximum, hence no rescaling, hence the two streams of a tile accumulate into ONE output accumulator
-//     O_t and ONE row-sum accumulator L_t (a sum is a sum), and there is nothing to merge in the epilogue;
-//   * a stream hands its score buffer back to the tensor pipe as soon as its warps have LOADED it (s_free), so its
-//     next scores S(t,i+2) are computed while it exponentiates S(t,i): the turn-around PV -> S -> softmax of the
-//     first four-stream version (980 of 2250 clk per stream iteration spent waiting) leaves the critical path.
+//     O_t and ONE row-sum accumulator L_t (a sum is a sum), and there is nothing to merge in the epilogue.
 //
 // Reference maximum: floating point is scale-invariant, so the online-softmax reference only has to prevent overflow,
 // not track the running maximum.  Each row takes the maximum of its FIRST sub-block as the reference for the whole row
@@ -471,15 +469,13 @@ __device__ __forceinline__ void attn_exact_body(const AttnShards& sh, const Attn
 // LayerNormed q/k, but constructible) makes the row sum or the output non-finite; the CTA then re-runs its 256 rows
 // through the exact path above in the same launch.  tests/test_kernels_gpu.py::test_attention_overflow_fixup.
 //
-// TMEM (512 columns) holds four score buffers, one P buffer per tile (the two streams of a tile take turns; PV(t,i-1)
-// has long completed when stream i&1 wants it), the two output accumulators and the row sums; Q stays in shared memory
-// (TMA, SWIZZLE_128B) and S = Q K^T is an SS-mode MMA.
-//   warps 0-15: softmax (stream w>>2 = 2t+b, TMEM quadrant w&3)   16: sub-block table, then TMA producer
-//   17: issuer of the score MMAs of both tiles   18, 19: issuers of the PV / row-sum MMAs of tile 0 and 1.  With their own
-//   buffers the scores and the PV products are independent instruction streams; one serial issuer per tile spent ~1290 clk
-//   per sub-block in barrier-wait latencies (~100 clk each, even when complete) and in issue slots blocked by the other
-//   tile's MMAs, and the softmax streams ran at its pace.
-//   TMEM columns: S(t,b) at 64(2t+b) [0,256) ; P_t at 256+32t [256,320) ; O_t at 320+64t [320,448) ;
+// Q is stored once into TMEM (bf16 pairs, one row per lane) by the softmax threads, so S = Q K^T runs as a TS-mode MMA
+// whose only shared-memory operand is the K sub-block: 32 clk per 128x64x16 instead of 48 (tools/mma_bench.cu).  P is
+// written in place over the first 32 columns of the stream's score buffer (only the writing warp ever reads those).
+//   warps 0-15: softmax (stream w>>2 = 2t+b, TMEM quadrant w&3)   16: builds the sub-block table   17: TMA producer
+//   18, 19: MMA issuers of query tile 0 and 1 (independent instruction streams; K/V ring stages are released by one
+//   commit from each).
+//   TMEM columns: S/P(t,b) at 64(2t+b) [0,256) ; O_t at 256+64t [256,384) ; Q_t at 384+32t [384,448) ;
 //                 L_t (row sums, 16 identical columns) at 448+16t [448,480)
 template <int KP, bool TRUNC, bool PROF>
 __global__ void __launch_bounds__(kAttnThreads, 1)
@@ -488,22 +484,18 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem + kOffK;
   uint8_t* sV = smem + kOffV;
-  uint8_t* sQ = smem + kOffQ;
   uint32_t* sOnes = reinterpret_cast<uint32_t*>(smem + kOffOnes);
   uint32_t* tab = reinterpret_cast<uint32_t*>(smem + kOffTab);
   float* sRef = reinterpret_cast<float*>(smem + kOffML);   // [tile][128] reference maximum * scale_log2
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBarsFast);
-  uint64_t* q_full = bars;               // 1
-  uint64_t* k_full = bars + 1;           // kKS
+  uint64_t* q_ready = bars;              // [tile] = 2
+  uint64_t* k_full = bars + 2;           // kKS
   uint64_t* k_empty = k_full + kKS;
   uint64_t* v_full = k_empty + kKS;
   uint64_t* v_empty = v_full + kKS;
   uint64_t* s_full = v_empty + kKS;      // [stream] = 4   S(t,i) is in TMEM
-  uint64_t* s_free = s_full + 4;         // [stream] = 4   the stream's warps hold S(t,i) in registers
-  uint64_t* p_full = s_free + 4;         // [tile] = 2     P(t,i) is in TMEM
-  uint64_t* p_free = p_full + 2;         // [tile][i&1] = 4  PV(t,i) has consumed the P buffer (one barrier per parity: a
-                                         //   stream may run two sub-blocks ahead of PV, a shared barrier's parity would alias)
-  uint64_t* all_done = p_free + 4;       // 1: every MMA of this CTA has completed
+  uint64_t* p_full = s_full + 4;         // [stream] = 4   P(t,i) is in TMEM
+  uint64_t* all_done = p_full + 4;       // 1: every MMA of this CTA has completed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffSlot);
 
   const int warp = threadIdx.x >> 5;
@@ -519,19 +511,17 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
       tma_prefetch_desc(&sh.k[s]);
       tma_prefetch_desc(&sh.v[s]);
     }
-    mbar_init(q_full, 1);
     for (int s = 0; s < kKS; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);   // the score issuer
+      mbar_init(&k_empty[s], 2);
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 2);   // the two PV issuers
+      mbar_init(&v_empty[s], 2);
     }
+    for (int i = 0; i < 2; ++i) mbar_init(&q_ready[i], 128);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 128);
+      mbar_init(&p_full[i], 128);
     }
-    for (int i = 0; i < 2; ++i) mbar_init(&p_full[i], 128);
-    for (int i = 0; i < 4; ++i) mbar_init(&p_free[i], 1);
     mbar_init(all_done, 2);
     fence_barrier_init();
   }
@@ -551,106 +541,103 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
   // back-to-back UTMALDG / UTCHMMA instead of a per-instruction divergence loop (measured: ~100 clk -> 32 clk).
   if (warp >= 16) reg_dealloc<56>();   // releases 4 x 32 x 40 = 5120 registers
   if (!p.exact_only) {
-    const uint32_t tab_s = smem_u32(tab);
-    auto tab_at = [&](int i) {   // explicit ld.shared (the generic pointer would compile to a generic LD)
-      uint32_t e;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(tab_s + 4u * uint32_t(i)));
-      return e;
-    };
-    if (warp == 16) {
-      // ------------------------------------------------------------------ TMA producer
-      if (elect_one()) {
-        mbar_expect_tx(q_full, 2 * kTileBytes);
-        tma_load_3d(sQ, &sh.q, q_full, 0, q0, bh);
-        tma_load_3d(sQ + kTileBytes, &sh.q, q_full, 0, q0 + 128, bh);
-      }
-      __syncwarp();
+    if (warp == 17) {
       produce_kv(sh, sK, sV, k_full, k_empty, v_full, v_empty, bh);
-    } else if (warp == 17) {
-      // ------------------------------------------------------------------ score issuer: S(t,i) = Q_t K_i^T, both tiles
-      const bool leader = elect_one();
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64);
-      const uint64_t qdesc = make_sdesc_sw128(smem_u32(sQ));
-      const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK));
-      long long w_k = 0, w_s = 0, i_s = 0, t_all = 0;
-      mbar_wait(q_full, 0);
-      if constexpr (PROF) t_all = clock64();
-      // S(t,i) goes into the buffer of stream (t, i&1) as soon as that stream holds S(t,i-2) in registers: scores run up
-      // to two sub-blocks per stream (four per tile) ahead of the softmax.  Descriptor address units are 16 B: ring
-      // stage = 1024, 64-row half = 512, query tile = 1024.
-      for (int i = 0; i < n_sub; ++i) {
-        const uint32_t e = tab_at(i);
-        const int st = tab_box(e) % kKS;
-        long long c0 = 0;
-        if constexpr (PROF) c0 = clock64();
-        if (tab_half(e) == 0) mbar_wait(&k_full[st], (tab_box(e) / kKS) & 1);
-        if constexpr (PROF) { const long long c1 = clock64(); w_k += c1 - c0; c0 = c1; }
-        const uint64_t bdesc = kdesc + uint32_t(st * (kTileBytes >> 4) + tab_half(e) * (kTileBytes >> 5));
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if constexpr (PROF) c0 = clock64();
-          if (i >= 2) mbar_wait(&s_free[2 * t + (i & 1)], ((i - 2) >> 1) & 1);
-          if constexpr (PROF) { const long long c1 = clock64(); w_s += c1 - c0; c0 = c1; }
-          tc_fence_after();
-          const uint64_t adesc = qdesc + uint32_t(t * (kTileBytes >> 4));
-          const uint32_t d = tmem_base + 128 * t + (i & 1) * 64;
-          if (leader) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-            umma_commit(&s_full[2 * t + (i & 1)]);
-          }
-          if constexpr (PROF) { __syncwarp(); i_s += clock64() - c0; }
-        }
-        if (leader && tab_last(e)) umma_commit(&k_empty[st]);
-      }
-      if constexpr (PROF) {
-        if (leader && p.prof != nullptr) {
-          long long* d = p.prof + ((int64_t)blockIdx.x * 20 + warp) * 8;
-          d[0] = w_k; d[1] = 0; d[2] = 0; d[3] = w_s; d[4] = i_s; d[5] = 0; d[6] = clock64() - t_all;
-        }
-      }
     } else if (warp >= 18) {
-      // ------------------------------------------------------------------ PV / row-sum issuer of query tile t
+      // ------------------------------------------------------------------ MMA issuer of query tile t
       const int t = warp - 18;
       const bool leader = elect_one();
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 64);
       constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);  // B (=V) is N-major
       constexpr uint32_t idesc_l = make_idesc_bf16(128, 16);               // row sums: P x ones[64 keys x 16]
+      const uint64_t kdesc = make_sdesc_sw128(smem_u32(sK));
       const uint64_t vdesc = make_sdesc_sw128(smem_u32(sV));
       const uint64_t odesc = make_sdesc_sw128(smem_u32(sOnes));
-      const uint32_t tm_p = tmem_base + 256 + 32 * t;
-      const uint32_t tm_o = tmem_base + 320 + 64 * t;
+      const uint32_t tm_s = tmem_base + 128 * t;        // S/P(t,0); S/P(t,1) 64 columns further
+      const uint32_t tm_o = tmem_base + 256 + 64 * t;
+      const uint32_t tm_q = tmem_base + 384 + 32 * t;
       const uint32_t tm_l = tmem_base + 448 + 16 * t;
-      long long w_v = 0, w_p = 0, i_pv = 0, t_all = 0;
-      if constexpr (PROF) t_all = clock64();
-      // O_t += P(t,i) V_i and L_t += P(t,i) 1 ; P: 128 lanes x 64 keys bf16 = 32 columns; 16 keys (8 columns) per MMA
-      for (int i = 0; i < n_sub; ++i) {
-        const uint32_t e = tab_at(i);
+      long long w_k = 0, w_v = 0, w_p = 0, i_s = 0, i_pv = 0, t_all = 0;
+      const uint32_t tab_s = smem_u32(tab);
+      auto tab_at = [&](int i) {   // explicit ld.shared (the generic pointer would compile to a generic LD)
+        uint32_t e;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(tab_s + 4u * uint32_t(i)));
+        return e;
+      };
+      // descriptor address units are 16 B: ring stage = 1024, 64-row half = 512
+      // S(t, i) = Q_t K_i^T into the buffer of stream (t, i&1); Q_t from TMEM (8 columns per 16-dim K step)
+      auto k_wait = [&](uint32_t e) {
+        if (tab_half(e) == 0) mbar_wait(&k_full[tab_box(e) % kKS], (tab_box(e) / kKS) & 1);
+      };
+      auto v_wait = [&](uint32_t e) {
+        if (tab_half(e) == 0) mbar_wait(&v_full[tab_box(e) % kKS], (tab_box(e) / kKS) & 1);
+      };
+      auto issue_s = [&](int i, uint32_t e) {
         const int st = tab_box(e) % kKS;
-        long long c0 = 0;
-        if constexpr (PROF) c0 = clock64();
-        if (tab_half(e) == 0) mbar_wait(&v_full[st], (tab_box(e) / kKS) & 1);
-        if constexpr (PROF) { const long long c1 = clock64(); w_v += c1 - c0; c0 = c1; }
-        mbar_wait(&p_full[t], i & 1);
-        if constexpr (PROF) { const long long c1 = clock64(); w_p += c1 - c0; c0 = c1; }
-        tc_fence_after();
+        const uint64_t bdesc = kdesc + uint32_t(st * (kTileBytes >> 4) + tab_half(e) * (kTileBytes >> 5));
+        const uint32_t d = tm_s + (i & 1) * 64;
+        if (leader) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_ts(d, tm_q + 8 * k, bdesc + 2 * k, idesc_s, k != 0);
+          umma_commit(&s_full[2 * t + (i & 1)]);
+          if (tab_last(e)) umma_commit(&k_empty[st]);
+        }
+      };
+      // O_t += P(t,i) V_i and L_t += P(t,i) 1 ; P: 128 lanes x 64 keys bf16 = the first 32 columns of the stream's score
+      // buffer; 16 keys (8 columns) per MMA
+      auto issue_pv = [&](int i, uint32_t e) {
+        const int st = tab_box(e) % kKS;
         const uint64_t bdesc = vdesc + uint32_t(st * (kTileBytes >> 4) + tab_half(e) * (kTileBytes >> 5));
+        const uint32_t a = tm_s + (i & 1) * 64;
         if (leader) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             // 16 keys per step: 16 rows x 128 B = 2048 B (encoded 128)
-            umma_ts(tm_o, tm_p + 8 * k, bdesc + 128 * k, idesc_o, (i | k) != 0);
-            umma_ts(tm_l, tm_p + 8 * k, odesc, idesc_l, (i | k) != 0);
+            umma_ts(tm_o, a + 8 * k, bdesc + 128 * k, idesc_o, (i | k) != 0);
+            umma_ts(tm_l, a + 8 * k, odesc, idesc_l, (i | k) != 0);
           }
-          umma_commit(&p_free[2 * t + (i & 1)]);
           if (tab_last(e)) umma_commit(&v_empty[st]);
         }
-        if constexpr (PROF) { __syncwarp(); i_pv += clock64() - c0; }
+      };
+      mbar_wait(&q_ready[t], 0);
+      if constexpr (PROF) t_all = clock64();
+      uint32_t e_pv = tab_at(0);                          // sub-block i (PV side)
+      uint32_t e_s = n_sub > 1 ? tab_at(1) : 0u;          // sub-block i + 1, then i + 2 (S side)
+      k_wait(e_pv);
+      tc_fence_after();
+      issue_s(0, e_pv);
+      if (n_sub > 1) {
+        k_wait(e_s);
+        tc_fence_after();
+        issue_s(1, e_s);
+      }
+      for (int i = 0; i < n_sub; ++i) {
+        const bool has_next = i + 2 < n_sub;
+        const uint32_t e_n = has_next ? tab_at(i + 2) : 0u;
+        // The K / V stages needed by this iteration landed long ago (the rings run four boxes ahead), but even a
+        // completed mbarrier wait costs ~100 clk of latency in this serial chain: take those waits BEFORE the wait for
+        // the softmax (P(t,i)), where they overlap with time spent waiting anyway.
+        long long c0 = 0;
+        if constexpr (PROF) c0 = clock64();
+        v_wait(e_pv);
+        if constexpr (PROF) { const long long c1 = clock64(); w_v += c1 - c0; c0 = c1; }
+        if (has_next) k_wait(e_n);
+        if constexpr (PROF) { const long long c1 = clock64(); w_k += c1 - c0; c0 = c1; }
+        mbar_wait(&p_full[2 * t + (i & 1)], (i >> 1) & 1);
+        if constexpr (PROF) { const long long c1 = clock64(); w_p += c1 - c0; c0 = c1; }
+        tc_fence_after();
+        issue_pv(i, e_pv);
+        if constexpr (PROF) { __syncwarp(); const long long c1 = clock64(); i_pv += c1 - c0; c0 = c1; }
+        if (has_next) issue_s(i + 2, e_n);   // same buffer as P(t,i): the tensor pipe executes in issue order
+        if constexpr (PROF) { __syncwarp(); i_s += clock64() - c0; }
+        e_pv = e_s;
+        e_s = e_n;
       }
       if (leader) umma_commit(all_done);
       if constexpr (PROF) {
         if (leader && p.prof != nullptr) {
           long long* d = p.prof + ((int64_t)blockIdx.x * 20 + warp) * 8;
-          d[0] = 0; d[1] = w_v; d[2] = w_p; d[3] = 0; d[4] = 0; d[5] = i_pv; d[6] = clock64() - t_all;
+          d[0] = w_k; d[1] = w_v; d[2] = w_p; d[3] = 0; d[4] = i_s; d[5] = i_pv; d[6] = clock64() - t_all;
         }
       }
     } else if (warp < 16) {
@@ -663,10 +650,29 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
       const int row_in_tile = quad * 32 + lane;
       const int q_row = q0 + t * 128 + row_in_tile;
       const uint32_t lane_base = uint32_t(quad * 32) << 16;
-      const uint32_t ts = tmem_base + lane_base + st * 64;         // S of this stream
-      const uint32_t tpp = tmem_base + lane_base + 256 + t * 32;   // P_t
-      const uint32_t to = tmem_base + lane_base + 320 + t * 64;    // O_t
+      const uint32_t ts = tmem_base + lane_base + st * 64;         // S / P of this stream
+      const uint32_t to = tmem_base + lane_base + 256 + t * 64;    // O_t
       const float sl2 = p.scale_log2;
+
+      if (b == 0) {
+        // Q row -> TMEM (bf16 pairs: column c holds dims 2c, 2c+1), zero beyond nq
+        uint32_t qr[32];
+        if (q_row < p.nq) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.q + ((int64_t)bh * p.q_rows + q_row) * 64);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint4 v = __ldg(src + c);
+            qr[4 * c] = v.x; qr[4 * c + 1] = v.y; qr[4 * c + 2] = v.z; qr[4 * c + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) qr[c] = 0u;
+        }
+        LD_TMEM_ST32(tmem_base + lane_base + 384 + 32 * t, qr);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&q_ready[t]);
+      }
 
       float msc = 0.f;   // reference maximum of the row (first sub-block) * scale_log2
       long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
@@ -681,9 +687,6 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
         LD_TMEM_LD32(ts, s);
         LD_TMEM_LD32(ts + 32, (s + 32));
         tmem_ld_wait();
-        // S(t,i) is in registers: hand the buffer back to the tensor pipe (S(t,i+2) runs under these exponentials)
-        tc_fence_before();
-        mbar_arrive(&s_free[st]);
         LD_PROF(1);
         const int valid = tab_valid(tab[i]);
         if (valid < 64) {
@@ -732,15 +735,10 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
           }
         }
         LD_PROF(3);
-        if (i > 0) {
-          // PV(t,i-1) of the sibling stream has consumed the tile's P buffer: its ((i-1)>>1)-th product
-          mbar_wait(&p_free[2 * t + (b ^ 1)], ((i - 1) >> 1) & 1);
-          tc_fence_after();
-        }
-        LD_TMEM_ST32(tpp, pk);
+        LD_TMEM_ST32(ts, pk);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&p_full[t]);
+        mbar_arrive(&p_full[st]);
         LD_PROF(4);
       }
       if (n_sub == 1 && b == 1) named_bar_sync(1 + t * 4 + quad, 64);   // pair barrier of a stream without any sub-block

@@ -67,15 +67,18 @@ __device__ __forceinline__ void row_stats(const float (*vals)[8], int nvec, int 
 
 // out = LN(x) * (1 + scale[seg]) + shift[seg], rows streamed through shared memory by bulk async copies.
 //
-// The first version (ln_modulate_kernel below, kept for D that does not fit) held a whole row in registers: 124 registers,
-// 24 % occupancy, and every warp's load -> reduce -> store phases in series — 2.7 TB/s of the 6.5 TB/s a copy reaches
-// (profiles/r1_ncu_rows.csv).  Here each warp owns a 3-deep ring of row buffers filled by cp.async.bulk (one elected
-// lane, mbarrier complete_tx), so 3 rows per warp (184 KB per SM for fp32 rows) are in flight regardless of what the
-// warp is doing, and the row is read from shared memory three times (mean, variance, output) instead of living in
-// registers.  Quads of 4 elements per lane and step: 16-byte (fp32) / 8-byte (bf16) conflict-free shared-memory reads,
+// The first version (ln_modulate_kernel below, kept for shapes this one cannot take) held a whole row in registers: 124
+// registers, 24 % occupancy, and every warp's load -> reduce -> store phases in series — 2.7 TB/s of the 6.5 TB/s a copy
+// reaches (profiles/r1_ncu_rows.csv).  Here each warp owns a contiguous range of rows and a 4-deep ring of row buffers
+// filled by cp.async.bulk (one elected lane, mbarrier complete_tx), so 4 rows per warp (184 KB per SM for fp32 rows) are
+// in flight regardless of what the warp is doing, and a row is read from shared memory three times (mean, variance,
+// output) instead of living in registers.  Rows are normalised in PAIRS: the four per-element parameter vectors (LN
+// weight / bias, adaLN scale / shift: 12 B per element, three times the bytes of a bf16 row, all L1 hits) are then
+// loaded once per two rows — the L1 / shared-memory pipe (128 B/clk/SM), not HBM, bounded the one-row-at-a-time variant
+// (3.1 TB/s).  Quads of 4 elements per lane and step: conflict-free 16-byte (fp32) / 8-byte (bf16) shared-memory reads,
 // 8-byte coalesced stores.
-constexpr int kLnStages = 3;
-constexpr int kLnWarps = 8;
+constexpr int kLnStages = 4;
+constexpr int kLnWarps = 6;
 
 template <typename TX>
 __device__ __forceinline__ float4 ld_quad(const TX* row, int q);
@@ -89,12 +92,81 @@ __device__ __forceinline__ float4 ld_quad<bf16>(const bf16* row, int q) {
   return make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
 }
 
+// mean / rstd of TWO rows at once: the two reduction chains (shared-memory reads, then 5 shuffle levels each) are
+// independent, so interleaving them hides half of the latency a single in-order warp would expose
+template <typename TX>
+__device__ __forceinline__ void ln_row_stats2(const TX* xa, const TX* xb, int nquad, int lane, float inv_d, float eps,
+                                              float& mean_a, float& rstd_a, float& mean_b, float& rstd_b) {
+  float sa = 0.f, sb = 0.f;
+#pragma unroll 8
+  for (int q = lane; q < nquad; q += 32) {
+    const float4 v = ld_quad<TX>(xa, q), u = ld_quad<TX>(xb, q);
+    sa += (v.x + v.y) + (v.z + v.w);
+    sb += (u.x + u.y) + (u.z + u.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  mean_a = sa * inv_d;
+  mean_b = sb * inv_d;
+  float qa = 0.f, qb = 0.f;
+#pragma unroll 8
+  for (int q = lane; q < nquad; q += 32) {
+    const float4 v = ld_quad<TX>(xa, q), u = ld_quad<TX>(xb, q);
+    const float d0 = v.x - mean_a, d1 = v.y - mean_a, d2 = v.z - mean_a, d3 = v.w - mean_a;
+    const float e0 = u.x - mean_b, e1 = u.y - mean_b, e2 = u.z - mean_b, e3 = u.w - mean_b;
+    qa = fmaf(d0, d0, qa); qa = fmaf(d1, d1, qa); qa = fmaf(d2, d2, qa); qa = fmaf(d3, d3, qa);
+    qb = fmaf(e0, e0, qb); qb = fmaf(e1, e1, qb); qb = fmaf(e2, e2, qb); qb = fmaf(e3, e3, qb);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    qa += __shfl_xor_sync(0xffffffffu, qa, o);
+    qb += __shfl_xor_sync(0xffffffffu, qb, o);
+  }
+  rstd_a = rsqrtf(qa * inv_d + eps);
+  rstd_b = rsqrtf(qb * inv_d + eps);
+}
+
+template <typename TX>
+__device__ __forceinline__ void ln_row_stats(const TX* xr, int nquad, int lane, float inv_d, float eps, float& mean,
+                                             float& rstd) {
+  float sum = 0.f;
+#pragma unroll 8
+  for (int q = lane; q < nquad; q += 32) {
+    const float4 v = ld_quad<TX>(xr, q);
+    sum += (v.x + v.y) + (v.z + v.w);
+  }
+  mean = warp_sum(sum) * inv_d;
+  float sq = 0.f;
+#pragma unroll 8
+  for (int q = lane; q < nquad; q += 32) {
+    const float4 v = ld_quad<TX>(xr, q);
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
+  }
+  rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
+}
+
+__device__ __forceinline__ uint2 ln_out_quad(const float4& v, float mean, float rstd, const uint2& wq, const uint2& bq,
+                                             const float4& sc, const float4& sh) {
+  const float y0 = fmaf((v.x - mean) * rstd, bf16_lo(wq.x), bf16_lo(bq.x));
+  const float y1 = fmaf((v.y - mean) * rstd, bf16_hi(wq.x), bf16_hi(bq.x));
+  const float y2 = fmaf((v.z - mean) * rstd, bf16_lo(wq.y), bf16_lo(bq.y));
+  const float y3 = fmaf((v.w - mean) * rstd, bf16_hi(wq.y), bf16_hi(bq.y));
+  uint2 o;
+  o.x = pack_bf16x2(fmaf(y0, 1.0f + sc.x, sh.x), fmaf(y1, 1.0f + sc.y, sh.y));
+  o.y = pack_bf16x2(fmaf(y2, 1.0f + sc.z, sh.z), fmaf(y3, 1.0f + sc.w, sh.w));
+  return o;
+}
+
 template <typename TX>
 __global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_bulk_kernel(
     const TX* __restrict__ x, bf16* __restrict__ out, const bf16* __restrict__ w, const bf16* __restrict__ b, float eps,
     const float* __restrict__ shift_img, const float* __restrict__ scale_img, const float* __restrict__ shift_txt,
     const float* __restrict__ scale_txt, int64_t mod_stride, int rows, int rows_per_batch, int tok_offset, int text_len,
-    int D) {
+    int D, int rows_per_warp) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,64 +174,83 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_bulk_kernel(
   uint8_t* ring = ln_smem + (size_t)warp * kLnStages * row_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)kLnWarps * kLnStages * row_bytes) + warp * kLnStages;
   const int nquad = D >> 2;
-  const int first = blockIdx.x * kLnWarps + warp;
-  const int stride = gridDim.x * kLnWarps;
+  const int64_t r0 = (int64_t)(blockIdx.x * kLnWarps + warp) * rows_per_warp;
+  const int64_t r1 = min((int64_t)rows, r0 + rows_per_warp);
   if (lane == 0) {
     for (int s = 0; s < kLnStages; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
     for (int s = 0; s < kLnStages; ++s) {
-      const int64_t r = (int64_t)first + (int64_t)s * stride;
-      if (r < rows) {
+      if (r0 + s < r1) {
         mbar_expect_tx(&bars[s], row_bytes);
-        bulk_load_1d(ring + s * row_bytes, x + r * D, row_bytes, &bars[s]);
+        bulk_load_1d(ring + s * row_bytes, x + (r0 + s) * D, row_bytes, &bars[s]);
       }
     }
   }
   __syncwarp();
   const float inv_d = 1.0f / (float)D;
-  int it = 0;
-  for (int64_t row = first; row < rows; row += stride, ++it) {
-    const int s = it % kLnStages;
-    mbar_wait(&bars[s], (it / kLnStages) & 1);
-    const TX* xr = reinterpret_cast<const TX*>(ring + s * row_bytes);
-    float sum = 0.f;
-    for (int q = lane; q < nquad; q += 32) {
-      const float4 v = ld_quad<TX>(xr, q);
-      sum += (v.x + v.y) + (v.z + v.w);
-    }
-    const float mean = warp_sum(sum) * inv_d;
-    float sq = 0.f;
-    for (int q = lane; q < nquad; q += 32) {
-      const float4 v = ld_quad<TX>(xr, q);
-      const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-      sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
-    }
-    const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
+  auto segment = [&](int64_t row, const float4*& shift, const float4*& scale) {
     const int bidx = (int)(row / rows_per_batch);
     const int t = (int)(row - (int64_t)bidx * rows_per_batch);
     const bool is_text = (tok_offset + t) < text_len;
-    const float4* shift = reinterpret_cast<const float4*>((is_text ? shift_txt : shift_img) + (int64_t)bidx * mod_stride);
-    const float4* scale = reinterpret_cast<const float4*>((is_text ? scale_txt : scale_img) + (int64_t)bidx * mod_stride);
-    uint2* orow = reinterpret_cast<uint2*>(out + row * D);
-    for (int q = lane; q < nquad; q += 32) {
-      const float4 v = ld_quad<TX>(xr, q);
-      const uint2 wq = __ldg(reinterpret_cast<const uint2*>(w) + q), bq = __ldg(reinterpret_cast<const uint2*>(b) + q);
-      const float4 sc = __ldg(scale + q), sh = __ldg(shift + q);
-      const float y0 = fmaf((v.x - mean) * rstd, bf16_lo(wq.x), bf16_lo(bq.x));
-      const float y1 = fmaf((v.y - mean) * rstd, bf16_hi(wq.x), bf16_hi(bq.x));
-      const float y2 = fmaf((v.z - mean) * rstd, bf16_lo(wq.y), bf16_lo(bq.y));
-      const float y3 = fmaf((v.w - mean) * rstd, bf16_hi(wq.y), bf16_hi(bq.y));
-      uint2 o;
-      o.x = pack_bf16x2(fmaf(y0, 1.0f + sc.x, sh.x), fmaf(y1, 1.0f + sc.y, sh.y));
-      o.y = pack_bf16x2(fmaf(y2, 1.0f + sc.z, sh.z), fmaf(y3, 1.0f + sc.w, sh.w));
-      orow[q] = o;
-    }
-    __syncwarp();   // every lane has finished reading this stage
-    const int64_t nxt = row + (int64_t)kLnStages * stride;
-    if (lane == 0 && nxt < rows) {
+    shift = reinterpret_cast<const float4*>((is_text ? shift_txt : shift_img) + (int64_t)bidx * mod_stride);
+    scale = reinterpret_cast<const float4*>((is_text ? scale_txt : scale_img) + (int64_t)bidx * mod_stride);
+  };
+  auto refill = [&](int it, int64_t row_done) {   // stage (it % kLnStages) has been read by every lane
+    const int64_t nxt = row_done + kLnStages;
+    if (lane == 0 && nxt < r1) {
+      const int s = it % kLnStages;
       fence_proxy_async_smem();   // generic-proxy reads of the stage are ordered before the async-proxy refill
       mbar_expect_tx(&bars[s], row_bytes);
       bulk_load_1d(ring + s * row_bytes, x + nxt * D, row_bytes, &bars[s]);
+    }
+  };
+  int it = 0;
+  int64_t row = r0;
+  while (row < r1) {
+    const int sa = it % kLnStages;
+    const TX* xa = reinterpret_cast<const TX*>(ring + sa * row_bytes);
+    const float4 *sh_a, *sc_a;
+    segment(row, sh_a, sc_a);
+    bool pair = row + 1 < r1;
+    const float4 *sh_b = sh_a, *sc_b = sc_a;
+    if (pair) {
+      segment(row + 1, sh_b, sc_b);
+      pair = (sh_b == sh_a) && (sc_b == sc_a);   // same sample and same text / image segment: the parameters are shared
+    }
+    mbar_wait(&bars[sa], (it / kLnStages) & 1);
+    if (pair) {
+      const int sb = (it + 1) % kLnStages;
+      mbar_wait(&bars[sb], ((it + 1) / kLnStages) & 1);
+      const TX* xb = reinterpret_cast<const TX*>(ring + sb * row_bytes);
+      float mean_a, rstd_a, mean_b, rstd_b;
+      ln_row_stats2<TX>(xa, xb, nquad, lane, inv_d, eps, mean_a, rstd_a, mean_b, rstd_b);
+      uint2* oa = reinterpret_cast<uint2*>(out + row * D);
+      uint2* ob = reinterpret_cast<uint2*>(out + (row + 1) * D);
+#pragma unroll 4
+      for (int q = lane; q < nquad; q += 32) {
+        const uint2 wq = __ldg(reinterpret_cast<const uint2*>(w) + q), bq = __ldg(reinterpret_cast<const uint2*>(b) + q);
+        const float4 sc = __ldg(sc_a + q), sh = __ldg(sh_a + q);
+        oa[q] = ln_out_quad(ld_quad<TX>(xa, q), mean_a, rstd_a, wq, bq, sc, sh);
+        ob[q] = ln_out_quad(ld_quad<TX>(xb, q), mean_b, rstd_b, wq, bq, sc, sh);
+      }
+      __syncwarp();
+      refill(it, row);
+      refill(it + 1, row + 1);
+      it += 2;
+      row += 2;
+    } else {
+      float mean_a, rstd_a;
+      ln_row_stats<TX>(xa, nquad, lane, inv_d, eps, mean_a, rstd_a);
+      uint2* oa = reinterpret_cast<uint2*>(out + row * D);
+#pragma unroll 4
+      for (int q = lane; q < nquad; q += 32) {
+        const uint2 wq = __ldg(reinterpret_cast<const uint2*>(w) + q), bq = __ldg(reinterpret_cast<const uint2*>(b) + q);
+        oa[q] = ln_out_quad(ld_quad<TX>(xa, q), mean_a, rstd_a, wq, bq, __ldg(sc_a + q), __ldg(sh_a + q));
+      }
+      __syncwarp();
+      refill(it, row);
+      it += 1;
+      row += 1;
     }
   }
 }
@@ -493,17 +584,21 @@ extern "C" int ld_layernorm_modulate(const void* x, int x_is_f32, void* out, con
       attr_set[dev][x_is_f32 ? 1 : 0] = true;
     }
     const int blocks_per_sm = smem <= 100 * 1024 ? 2 : 1;
-    const int grid = grid_for(rows, kLnWarps, sm_count() * blocks_per_sm);
+    // every warp owns a contiguous range of rows (so the two rows of a pair share their parameters almost always)
+    const int max_warps = sm_count() * blocks_per_sm * kLnWarps;
+    int rows_per_warp = (rows + max_warps - 1) / max_warps;
+    if (rows_per_warp < 2) rows_per_warp = 2;
+    const int grid = (rows + rows_per_warp * kLnWarps - 1) / (rows_per_warp * kLnWarps);
     if (x_is_f32)
       ln_modulate_bulk_kernel<float><<<grid, kLnWarps * 32, smem, st>>>((const float*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
                                                                          eps, shift_img, scale_img, shift_txt, scale_txt,
                                                                          mod_batch_stride, rows, rows_per_batch, tok_offset,
-                                                                         text_len, D);
+                                                                         text_len, D, rows_per_warp);
     else
       ln_modulate_bulk_kernel<bf16><<<grid, kLnWarps * 32, smem, st>>>((const bf16*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
                                                                         eps, shift_img, scale_img, shift_txt, scale_txt,
                                                                         mod_batch_stride, rows, rows_per_batch, tok_offset,
-                                                                        text_len, D);
+                                                                        text_len, D, rows_per_warp);
     LD_CHECK_CUDA(cudaGetLastError());
     return LD_OK;
   }

@@ -1,0 +1,90 @@
+"""CUDA-graphed network evaluation (the engine / sampler glue on device).
+
+One denoising step of the drop-in network is ~350 kernel launches issued from Python through ctypes, each encoding two or
+three TMA descriptors on the host (~25 us apiece).  Nothing in them depends on host state that changes from step to step:
+every operand lives in a persistent workspace, the per-step scalars (the timestep) arrive through a device tensor.  So the
+whole `ControlDiffWarp` forward — control net + main net, all GEMMs, attention launches and row kernels — is captured
+ONCE per input shape into a CUDA graph and replayed for each of the 50 sampler steps (reference loop:
+sgm/modules/diffusionmodules/sampling.py:785-837, which re-enters Python modules every step).  The fused sampler update
+stays outside the graph: its coefficients are host scalars that differ per step, and it is a single launch.
+
+Not graphed: the sequence-parallel layouts (4 / 8 GPUs).  Their attention launches carry per-call transfer ids of the
+copy-engine K|V exchange (landiff_b200/dma_ring.py), which a replay would repeat.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import dit
+
+
+class GraphedWarp:
+    """Wraps a `ControlDiffWarp` (or any network with its call signature); the first call for a given input signature
+    runs eagerly twice (allocating workspaces, loading modules) and captures, later calls copy the inputs into the
+    captured buffers and replay.  The returned tensor is the network's persistent output buffer, exactly like the eager
+    path."""
+
+    def __init__(self, warp, warmup: int = 2):
+        if getattr(warp, "owned_latent_mask", None) is not None:
+            raise RuntimeError("sequence-parallel networks are not graph-captured (per-call transfer ids); use the eager path")
+        self.warp = warp
+        self.warmup = warmup
+        self._graphs: Dict[tuple, dict] = {}
+        self.replays = 0
+
+    def __getattr__(self, name):  # e.g. .main_model / .control_model / .parameters()
+        return getattr(self.__dict__["warp"], name)
+
+    def _semantic(self):
+        return dit._registry().get_value("semantic_feature")
+
+    def __call__(self, x: torch.Tensor, t: torch.Tensor, c: dict, **kwargs) -> torch.Tensor:
+        ctx = c.get("crossattn")
+        sem = self._semantic()
+        if sem is None or ctx is None:
+            return self.warp(x, t, c, **kwargs)   # let the eager path raise its own, precise error
+        key = (tuple(x.shape), x.dtype, tuple(ctx.shape), ctx.dtype, tuple(sem.shape), sem.dtype, str(x.device))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture(key, x, t, ctx, sem)
+        g["x"].copy_(x, non_blocking=True)
+        g["t"].copy_(t.reshape(-1).to(torch.float32), non_blocking=True)
+        g["ctx"].copy_(ctx, non_blocking=True)
+        g["sem"].copy_(sem, non_blocking=True)   # the registry is only read at capture time; replays use this buffer
+        g["graph"].replay()
+        self.replays += 1
+        return g["out"]
+
+    def _capture(self, key, x, t, ctx, sem):
+        s = dict(x=x.clone(), t=t.reshape(-1).to(torch.float32).clone(), ctx=ctx.clone(), sem=sem.clone())
+        reg = dit._registry()
+
+        def run():
+            reg.register("semantic_feature", s["sem"])
+            try:
+                return self.warp(s["x"], s["t"], {"crossattn": s["ctx"]}, idx=s["t"])
+            finally:
+                reg.register("semantic_feature", sem)
+
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                run()
+        torch.cuda.current_stream(x.device).wait_stream(side)
+        torch.cuda.synchronize(x.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = run()
+        s.update(graph=graph, out=out)
+        self._graphs[key] = s
+        return s
+
+
+def maybe_graph(warp, enable: bool = True):
+    """GraphedWarp when the layout allows it (no sequence parallelism), else the network itself."""
+    if not enable or getattr(warp, "owned_latent_mask", None) is not None:
+        return warp
+    return GraphedWarp(warp)
