@@ -129,6 +129,18 @@ def run_ours(args):
     net = warp
     sampler = VPSDEDPMPP2MSampler(num_steps=SAMPLER_STEPS, device="cuda")
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if args.workload == "stream3":
+        run_stream3(args, world, rank, dev, layout, warp, cfg, cfg_group, barrier)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
     g = torch.Generator().manual_seed(1)
     x_host = torch.randn(1, cfg.latent_t, cfg.in_channels, cfg.latent_h, cfg.latent_w, generator=g).pin_memory()
     ctx_host = (torch.randn(1, cfg.text_length, cfg.text_hidden, generator=g) * 0.2).to(torch.bfloat16).pin_memory()
@@ -158,11 +170,6 @@ def run_ours(args):
     ops.attention = timed(ops.attention)                  # single-buffer launch (1 and 2 GPUs)
     ops.attention_shards = timed(ops.attention_shards)    # multi-shard launch of the sequence-parallel layouts
     timed_attention = timed
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def sample_k(x0, k, start=0):
         """k consecutive sampler steps of the 50-step schedule (wrapping around for k > 50)."""
@@ -230,14 +237,12 @@ def run_ours(args):
         host_graph = (time.perf_counter() - h0) / g_steps * 1e3     # host time to ENQUEUE a step (no sync inside)
         barrier()
         l_graph = (_C.LAUNCHES[0] - l0) / g_steps
-        h0 = time.perf_counter()
-        sampler.sample(warp, x_dev, cond, uc, cfg_group=cfg_group, start_step=0, max_steps=g_steps)
-        host_eager = (time.perf_counter() - h0) / g_steps * 1e3
-        barrier()
         graph_info = {"ms_per_step": round(g0.elapsed_time(g1) / g_steps, 3), "steps_timed": g_steps,
-                      "host_enqueue_ms_per_step_graph": round(host_graph, 3),
-                      "host_enqueue_ms_per_step_eager": round(host_eager, 3),
-                      "c_abi_calls_per_step_graph": l_graph, "replays": gw.replays}
+                      "host_enqueue_ms_per_step": round(host_graph, 3),
+                      "c_abi_calls_per_step": l_graph, "c_abi_calls_per_step_eager": launches / args.steps,
+                      "replays": gw.replays,
+                      "what": "one CUDA-graph replay of the whole ControlDiffWarp forward + the fused sampler update per step; "
+                              "host_enqueue = host time to enqueue a step (no sync inside the loop)"}
 
     status = ops.attention_status()
     t = torch.tensor([ms, e2e_ms, float(status)], device=dev, dtype=torch.float64)
@@ -298,6 +303,78 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------- config 5
+def run_stream3(args, world, rank, dev, layout, warp, cfg, cfg_group, barrier):
+    """BASELINE config 5: streaming long-video diffusion, 3 chained 49-frame chunks (13 latent frames each; chunks 2 and 3
+    keep the last 7 latent frames of their predecessor as a fixed prefix and receive their own semantic features), 50
+    DPM++ CFG steps per chunk, full shape — landiff_b200/streaming.py over the reference's hooks
+    (sampling.py:800-835, diffusion_video.py:287-288, ...video_vq.yaml:213,231).  Prints its own JSON line."""
+    import torch.distributed as dist
+
+    from landiff_b200 import _C, dit, ops
+    from landiff_b200.sampling import VPSDEDPMPP2MSampler
+    from landiff_b200.streaming import StreamPlan, sample_stream
+
+    plan = StreamPlan(n_chunks=3, chunk_frames=cfg.latent_t, prefix_frames=7)
+    g = torch.Generator().manual_seed(5)
+    ctx_host = (torch.randn(1, cfg.text_length, cfg.text_hidden, generator=g) * 0.2).to(torch.bfloat16).pin_memory()
+    sem_host = [(torch.randn(1, cfg.latent_t, cfg.in_channels, cfg.latent_h, cfg.latent_w, generator=g) * 0.1).to(torch.bfloat16).pin_memory()
+                for _ in range(plan.n_chunks)]
+    out_host = torch.empty(1, plan.total_frames, cfg.in_channels, cfg.latent_h, cfg.latent_w).pin_memory()
+
+    def register(feat):
+        dit.InferValueRegistry.clear()
+        dit.InferValueRegistry.register("semantic_feature", feat)
+
+    def one_stream(steps_per_chunk):
+        cond = {"crossattn": ctx_host.to(dev, non_blocking=True)}                     # H2D: text features
+        uc = {"crossattn": torch.zeros_like(cond["crossattn"])}
+        feats = [f.to(dev, non_blocking=True) for f in sem_host]                      # H2D: per-chunk semantic features
+        mk = lambda k: VPSDEDPMPP2MSampler(num_steps=steps_per_chunk, device="cuda", fixed_frames=k)
+        z = sample_stream(warp, mk, plan, (cfg.in_channels, cfg.latent_h, cfg.latent_w), cond, uc, feats, register, device=dev,
+                          cfg_group=cfg_group)
+        out_host.copy_(z, non_blocking=True)                                         # D2H: the stitched latent
+        return z
+
+    torch.manual_seed(42)
+    barrier()
+    one_stream(2)                    # warm-up: every kernel / buffer / peer mapping of the layout
+    barrier()
+    clocks = ClockSampler(dev.index or 0)
+    if rank == 0:
+        clocks.start()
+    l0 = _C.LAUNCHES[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    z = one_stream(SAMPLER_STEPS)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _C.LAUNCHES[0] - l0
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms, float(ops.attention_status()), float(torch.isfinite(z).all())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        n_steps = plan.n_chunks * SAMPLER_STEPS
+        line = {"metric": "seconds per streamed 3 x 49-frame 480x720 video (3 chained chunks, 50-step CFG denoise each)",
+                "value": round(float(t[0]) / 1e3, 4), "unit": UNIT, "n_gpus": world, "steps": n_steps, "warmup": 6,
+                "ms_per_step": round(float(t[0]) / n_steps, 3), "higher_is_better": False, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "stream3: BASELINE config 5 — 3 chained chunks of 13 latent frames (49 video frames) at "
+                                       "480x720, 7-latent-frame fixed prefix from the previous chunk, per-chunk semantic features, "
+                                       f"{plan.total_frames} latent frames = {plan.video_frames()} video frames in total",
+                           "parallelism": {1: "single GPU", 2: "cfg2", 4: "cfg2 x sp2", 8: "cfg2 x sp4"}.get(world, "?"),
+                           "l2": "per-step working set (>6 GB) exceeds the 126 MB L2; no explicit flush"},
+                "e2e": {"value": round(float(t[0]) / 1e3, 4), "unit": UNIT,
+                        "h2d_bytes_per_step": (ctx_host.numel() * 2 + sum(f.numel() * 2 for f in sem_host)) // n_steps,
+                        "d2h_bytes_per_step": out_host.numel() * 4 // n_steps,
+                        "note": "the timed region IS end to end: host text / semantic features in, stitched latent out"},
+                "gpu_launches": launches, "shard_wait_timeouts": int(t[1]), "finite": bool(t[2]), "clocks": clk}
+        print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------- B2: eager GPU
@@ -405,6 +482,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="denoise", choices=["denoise", "stream3"],
+                    help="denoise: BASELINE configs 2-4 (one 49-frame video); stream3: config 5 (3 chained chunks)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-eager", action="store_true", help="skip the PyTorch-eager bf16 GPU baseline leg (N = 1)")
     args = ap.parse_args()

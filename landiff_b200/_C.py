@@ -112,11 +112,14 @@ class LanDiffB200Error(RuntimeError):
     pass
 
 
-LAUNCHES = [0]  # kernels launched through the C-ABI (every compute entry point launches exactly one kernel)
+LAUNCHES = [0]  # KERNELS launched through the C-ABI (every compute entry point launches exactly one kernel)
+# entry points that launch no kernel: queries, allocation, copy-engine copies and stream memory operations
+_NO_KERNEL = {"ld_device_check", "ld_ipc_alloc", "ld_ipc_open", "ld_ipc_close", "ld_ipc_free", "ld_copy_async",
+              "ld_stream_write_u32", "ld_stream_wait_geq_u32", "ld_attention_status", "w"}
 
 
 def check(rc: int, what: str) -> None:
-    if rc == LD_OK and what != "ld_device_check":
+    if rc == LD_OK and what not in _NO_KERNEL:
         LAUNCHES[0] += 1
     if rc != LD_OK:
         msg = load().ld_last_error().decode(errors="replace")
