@@ -45,6 +45,24 @@ def peaks():
         return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_dram_bytes(csv_path, kernel_substr):
+    """(dram__bytes_read.sum + dram__bytes_write.sum in bytes, source) of the first kernel whose name contains
+    `kernel_substr` in a tools/ncu_summary.py CSV; (None, why) when the file or the columns are missing."""
+    import csv
+
+    try:
+        rows = list(csv.reader(open(csv_path)))
+        hdr, units = rows[0], rows[1]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for r in rows[2:]:
+            if kernel_substr in r[0]:
+                return float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]], f"profiles/{Path(csv_path).name}"
+        return None, f"{kernel_substr} not in {csv_path}"
+    except Exception as e:  # noqa: BLE001
+        return None, f"unavailable: {e}"
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
 
@@ -258,11 +276,14 @@ def run_ours(args):
         nq = cfg.n_tok // layout.sp_size
         flop_per_launch = 4.0 * nq * cfg.n_tok * 64 * b_rows * cfg.num_heads   # this rank's queries x ALL keys (one launch)
         attn_avg = sum(attn_ms) / max(len(attn_ms), 1)
-        # DRAM traffic of one attention launch from the `ncu --set full` capture of the same kernel and shape at B = 1
-        # (profiles/r1_ncu_attn4.csv: dram__bytes_read.sum 205.7 MB + dram__bytes_write.sum 51.6 MB); the launch is
+        # DRAM traffic of one attention launch: dram__bytes_read.sum + dram__bytes_write.sum of the `ncu --set full` capture
+        # of the shipped kernel at the same shape and B = 1 (read from profiles/r2_ncu_attn5.csv); the launch is
         # independent per batch row, so B rows move B times that.  Algorithmic bytes (Q, K, V in, O out) = 273 MB per
-        # row: K/V re-reads of the 70 query blocks of a head are served by L2 (hit rate 94.7 %).  Ring shards: no capture.
-        traffic = 257.2e6 * b_rows if layout.sp_size == 1 else None
+        # row: K/V re-reads of the 70 query blocks of a head are served by L2.  Sequence-parallel shards: no capture.
+        traffic, traffic_src = None, None
+        if layout.sp_size == 1:
+            traffic, traffic_src = ncu_dram_bytes(ROOT / "profiles" / "r2_ncu_attn5.csv", "attn5_kernel")
+            traffic = traffic * b_rows if traffic is not None else None
         achieved = flop_per_launch / (attn_avg * 1e-3) / 1e12 if attn_avg > 0 else 0.0
         line = {
             "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -280,7 +301,7 @@ def run_ours(args):
                                    + ("" if layout.sp_size == 1 else f"; one launch over {layout.sp_size} K/V shards, arrival flags polled in-kernel") + ")",
                          "achieved": round(achieved, 1), "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": round(achieved / tf_peak, 4), "traffic": traffic,
-                         "traffic_unit": "bytes per launch (ncu dram read + write, profiles/r1_ncu_attn4.csv)",
+                         "traffic_unit": f"bytes per launch (ncu dram read + write at B = 1 x batch rows, {traffic_src})",
                          "peak_source": how,
                          "launch_ms": round(attn_avg, 4), "launches_timed": len(attn_ms),
                          "share_of_step": round(sum(attn_ms) / ms, 4) if ms > 0 else None},

@@ -10,6 +10,7 @@
 // The fused epilogues implement the reference's per-layer elementwise work (bias, GELU-tanh, adaLN-gated
 // residual, control add, QKV split + per-head QK-LayerNorm, patch-embed position add, unpatchify); see
 // include/landiff_b200.h for the reference lines each one replaces.
+#include <cstdlib>
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -420,6 +421,226 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// CTA-pair GEMM (round 2): 256 x 192 output tiles computed by two CTAs of a cluster with tcgen05.mma.cta_group::2.
+//
+// With 128 x 192 tiles one k-block of 64 moves (128 + 192) x 128 B = 40 KB from L2 into shared memory for 3.1 MFLOP —
+// 78 FLOP per byte, i.e. ~17 TB/s of L2 -> SM traffic at 1330 TFLOP/s, which is what the fabric delivers: the 1-CTA kernel
+// sits at 0.76-0.89 of the measured cuBLAS peak with its tensor pipe 70-90 % busy (profiles/r1_ncu_gemm_v2.csv).  A CTA
+// pair shares the W tile: each CTA loads its 128 rows of A and HALF of the W tile (96 rows), the UMMA reads both halves
+// from the two shared memories -> 28 KB per CTA and k-block, 112 FLOP per byte, and room for 7 stages instead of 5.
+//   per CTA: warp 0 TMA producer (both CTAs), warp 1 MMA issuer (leader CTA only), warps 2..9 epilogue (own 128 rows)
+//   full[s]   leader's barrier: ONE arrival, the leader's arrive.expect_tx of the bytes of BOTH CTAs.  The peer's TMA
+//             completes on it too but does not arrive: a remote mbarrier.arrive per k-block costs a cluster-scope release
+//             fence (MEMBAR + ERRBAR, ~5 % of all stall samples and a producer slower than the MMAs — measured, 605
+//             TFLOP/s).  Bytes of the peer that land before the leader's expect_tx only drive the pending count negative;
+//             they cannot complete a phase (the leader's arrival is still outstanding) and cannot hit the previous phase
+//             (the peer refills a stage only after the multicast commit of the MMAs that consumed it).
+//   empty[s], tfull[a]   one per CTA, signalled in both by multicast tcgen05.commit
+//   tempty[a] leader's barrier: 8 epilogue warps of each CTA arrive (the peer's through mapa)
+struct Gemm2Cfg {
+  static constexpr int BN = 192;
+  static constexpr int BM = 128;           // rows per CTA; 256 per pair
+  static constexpr int BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 7;
+  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr int ACC_STRIDE = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const ld_gemm_args p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + Cfg::STAGES;
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();      // 0 = leader
+  const bool is_leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 16);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();      // barrier inits and TMEM allocations of both CTAs are visible before any remote access
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m2 = (p.M + 2 * Cfg::BM - 1) / (2 * Cfg::BM);   // 256-row pair tiles
+  const int num_n = p.N / BN;
+  const int num_tiles = num_m2 * num_n;
+  const int num_kb = p.K / Cfg::BK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    const bool leader_lane = elect_one();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / num_n) * (2 * Cfg::BM) + (int)rank * Cfg::BM;
+      const int n0 = (tile % num_n) * BN + (int)rank * (BN / 2);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (leader_lane) {
+          const uint32_t full0 = mapa_shared(smem_u32(&full_bar[s]), 0);   // the leader's full barrier
+          if (is_leader) mbar_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_2cta(sA + s * Cfg::A_BYTES, &tmap_a, full0, kb * Cfg::BK, m0);
+          tma_load_2d_2cta(sB + s * Cfg::B_BYTES, &tmap_b, full0, kb * Cfg::BK, n0);
+        }
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (is_leader) {
+      const bool leader_lane = elect_one();
+      constexpr uint32_t idesc = make_idesc_bf16(2 * Cfg::BM, BN);
+      const uint64_t adesc0 = make_sdesc_sw128(smem_u32(sA));
+      const uint64_t bdesc0 = make_sdesc_sw128(smem_u32(sB));
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tempty_bar[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t adesc = adesc0 + uint32_t(s * (Cfg::A_BYTES >> 4));
+          const uint64_t bdesc = bdesc0 + uint32_t(s * (Cfg::B_BYTES >> 4));
+          if (leader_lane) {
+#pragma unroll
+            for (int k = 0; k < Cfg::BK / 16; ++k)
+              umma_ss_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(&empty_bar[s]);
+          }
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+        if (leader_lane) umma_commit_2cta(&tfull_bar[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (each CTA: its own 128 rows)
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    constexpr int kSplit = (EPI == LD_EPI_QKV) ? 64 : 96;
+    const int c_begin = half == 0 ? 0 : kSplit;
+    const int c_end = half == 0 ? kSplit : BN;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / num_n) * (2 * Cfg::BM) + (int)rank * Cfg::BM;
+      const int n0 = (tile % num_n) * BN;
+      RowCtx rc;
+      rc.row = m0 + row_in_tile;
+      rc.valid = rc.row < p.M;
+      const int rr = rc.valid ? rc.row : 0;
+      rc.b = rr / p.rows_per_batch;
+      rc.t = rr - rc.b * p.rows_per_batch;
+      rc.is_text = (p.tok_offset + rc.t) < p.text_len;
+      rc.out_row = (int64_t)rc.b * p.out_rows_per_batch + p.out_row_offset + rc.t;
+
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quad * 32) << 16) + as * Cfg::ACC_STRIDE;
+      if constexpr (EPI == LD_EPI_QKV) {
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; c += 64) {
+          uint32_t r0[32], r1[32];
+          LD_TMEM_LD32(taddr + c, r0);
+          LD_TMEM_LD32(taddr + c + 32, r1);
+          tmem_ld_wait();
+          epilogue_qkv64(p, rc, n0 + c, r0, r1);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; c += 32) {
+          EpiOperands<EPI> ops;
+          epi_fetch<EPI>(p, rc, n0 + c, ops);
+          uint32_t r[32];
+          LD_TMEM_LD32(taddr + c, r);
+          tmem_ld_wait();
+          epilogue32<EPI>(p, rc, n0 + c, r, ops);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[as]), 0));   // the leader's MMA warp waits
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();      // no CTA leaves (or frees TMEM) while its partner may still touch its shared memory / TMEM
+  if (warp == 1) tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+}
+
+template <int EPI>
+static int launch_gemm2(const ld_gemm_args& a, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg;
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+    const uint64_t str[1] = {(uint64_t)a.K * 2};
+    const uint32_t box[2] = {64, 128};
+    int rc = make_tmap_bf16(&ta, a.A, 2, dims, str, box);
+    if (rc != LD_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+    const uint64_t str[1] = {(uint64_t)a.K * 2};
+    const uint32_t box[2] = {64, (uint32_t)(Cfg::BN / 2)};
+    int rc = make_tmap_bf16(&tb, a.W, 2, dims, str, box);
+    if (rc != LD_OK) return rc;
+  }
+  auto kern = gemm2_kernel<EPI>;
+  static bool attr_set[64] = {false};  // per template instantiation and device
+  int dev = 0;
+  LD_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set[dev] = true;
+  }
+  const int num_tiles = ((a.M + 255) / 256) * (a.N / Cfg::BN);
+  const int max_clusters = sm_count() / 2;
+  const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+  kern<<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(ta, tb, a);
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}
+
 template <int BN, int EPI>
 static int launch_gemm(const ld_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -451,8 +672,21 @@ static int launch_gemm(const ld_gemm_args& a, cudaStream_t stream) {
   return LD_OK;
 }
 
+static bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LD_GEMM_1CTA");   // tuning / A-B switch: force the 1-CTA kernel
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <int EPI>
 static int dispatch_bn(const ld_gemm_args& a, cudaStream_t stream) {
+  if constexpr (EPI != LD_EPI_UNPATCHIFY && EPI != LD_EPI_BIAS_POS) {
+    // the five per-layer GEMMs (QKV, out-proj, fc1, fc2, zero-linear): CTA pairs, 256 x 192 tiles
+    if (a.N % 192 == 0 && a.M >= 256 && use_pair_kernel()) return launch_gemm2<EPI>(a, stream);
+  }
   if (a.N % 192 == 0) return launch_gemm<192, EPI>(a, stream);
   if (a.N % 128 == 0) return launch_gemm<128, EPI>(a, stream);
   return launch_gemm<64, EPI>(a, stream);
