@@ -660,10 +660,12 @@ static int launch_gemm(const ld_gemm_args& a, cudaStream_t stream) {
     if (rc != LD_OK) return rc;
   }
   auto kern = gemm_kernel<BN, EPI>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
+  static bool attr_set[64] = {false};  // per template instantiation and device
+  int dev = 0;
+  LD_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int num_tiles = ((a.M + 127) / 128) * (a.N / BN);
   const int grid = num_tiles < sm_count() ? num_tiles : sm_count();

@@ -68,113 +68,61 @@ __device__ __forceinline__ void row_stats(const float (*vals)[8], int nvec, int 
 // out = LN(x) * (1 + scale[seg]) + shift[seg], rows streamed through shared memory by bulk async copies.
 //
 // The first version (ln_modulate_kernel below, kept for shapes this one cannot take) held a whole row in registers: 124
-// registers, 24 % occupancy, and every warp's load -> reduce -> store phases in series — 2.7 TB/s of the 6.5 TB/s a copy
-// reaches (profiles/r1_ncu_rows.csv).  Here each warp owns a contiguous range of rows and a 4-deep ring of row buffers
-// filled by cp.async.bulk (one elected lane, mbarrier complete_tx), so 4 rows per warp (184 KB per SM for fp32 rows) are
-// in flight regardless of what the warp is doing, and a row is read from shared memory three times (mean, variance,
-// output) instead of living in registers.  Rows are normalised in PAIRS: the four per-element parameter vectors (LN
-// weight / bias, adaLN scale / shift: 12 B per element, three times the bytes of a bf16 row, all L1 hits) are then
-// loaded once per two rows — the L1 / shared-memory pipe (128 B/clk/SM), not HBM, bounded the one-row-at-a-time variant
-// (3.1 TB/s).  Quads of 4 elements per lane and step: conflict-free 16-byte (fp32) / 8-byte (bf16) shared-memory reads,
-// 8-byte coalesced stores.
+// registers, 24 % occupancy, every warp's load -> reduce -> store phases in series — 2.7 TB/s of the 6.5 TB/s a copy reaches
+// (profiles/r1_ncu_rows.csv).  Moving the rows into a cp.async.bulk ring alone changed little (3.0 TB/s): ncu showed no
+// unit above 47 % — the kernel was INSTRUCTION bound, ~13 thread-instructions per element (bf16 unpack, four separate
+// parameter vectors, scalar math) against a budget of ~8 at HBM speed.  This version
+//   * folds the four parameter vectors into two per (sample, segment), A = w (1 + scale) and C = b (1 + scale) + shift, built
+//     once per CTA in shared memory (a CTA's contiguous row range touches at most two such combinations; a third falls
+//     back to the register kernel's arithmetic from global memory), so that out = (x g + h) A + C with the row scalars
+//     g = rstd, h = -mean rstd: two packed FFMA2 per element pair;
+//   * uses packed f32x2 adds / FMAs for the statistics as well (mean, then sum of squared deviations: two passes over the
+//     shared-memory copy, same arithmetic as nn.LayerNorm);
+//   * gives each warp a contiguous range of rows and a 4-deep ring of row buffers filled by cp.async.bulk (one elected
+//     lane, mbarrier complete_tx): rows in flight do not depend on what the warp is doing.
+// Quads of 4 elements per lane and step: conflict-free 16-byte (fp32) / 8-byte (bf16) shared-memory reads, 8-byte coalesced
+// stores.
 constexpr int kLnStages = 4;
-constexpr int kLnWarps = 6;
 
 template <typename TX>
-__device__ __forceinline__ float4 ld_quad(const TX* row, int q);
+struct LnCfg;
 template <>
-__device__ __forceinline__ float4 ld_quad<float>(const float* row, int q) {
-  return reinterpret_cast<const float4*>(row)[q];
+struct LnCfg<float> { static constexpr int kWarps = 6; };     // 6 x 4 x 7.5 KB rows + 30 KB tables = 210 KB
+template <>
+struct LnCfg<bf16> { static constexpr int kWarps = 12; };     // 12 x 4 x 3.75 KB rows + 30 KB tables = 210 KB
+
+template <typename TX>
+__device__ __forceinline__ void ld_quad2(const TX* row, int q, uint64_t& lo, uint64_t& hi);
+template <>
+__device__ __forceinline__ void ld_quad2<float>(const float* row, int q, uint64_t& lo, uint64_t& hi) {
+  const ulonglong2 v = reinterpret_cast<const ulonglong2*>(row)[q];
+  lo = v.x;
+  hi = v.y;
 }
 template <>
-__device__ __forceinline__ float4 ld_quad<bf16>(const bf16* row, int q) {
+__device__ __forceinline__ void ld_quad2<bf16>(const bf16* row, int q, uint64_t& lo, uint64_t& hi) {
   const uint2 v = reinterpret_cast<const uint2*>(row)[q];
-  return make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
-}
-
-// mean / rstd of TWO rows at once: the two reduction chains (shared-memory reads, then 5 shuffle levels each) are
-// independent, so interleaving them hides half of the latency a single in-order warp would expose
-template <typename TX>
-__device__ __forceinline__ void ln_row_stats2(const TX* xa, const TX* xb, int nquad, int lane, float inv_d, float eps,
-                                              float& mean_a, float& rstd_a, float& mean_b, float& rstd_b) {
-  float sa = 0.f, sb = 0.f;
-#pragma unroll 8
-  for (int q = lane; q < nquad; q += 32) {
-    const float4 v = ld_quad<TX>(xa, q), u = ld_quad<TX>(xb, q);
-    sa += (v.x + v.y) + (v.z + v.w);
-    sb += (u.x + u.y) + (u.z + u.w);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    sa += __shfl_xor_sync(0xffffffffu, sa, o);
-    sb += __shfl_xor_sync(0xffffffffu, sb, o);
-  }
-  mean_a = sa * inv_d;
-  mean_b = sb * inv_d;
-  float qa = 0.f, qb = 0.f;
-#pragma unroll 8
-  for (int q = lane; q < nquad; q += 32) {
-    const float4 v = ld_quad<TX>(xa, q), u = ld_quad<TX>(xb, q);
-    const float d0 = v.x - mean_a, d1 = v.y - mean_a, d2 = v.z - mean_a, d3 = v.w - mean_a;
-    const float e0 = u.x - mean_b, e1 = u.y - mean_b, e2 = u.z - mean_b, e3 = u.w - mean_b;
-    qa = fmaf(d0, d0, qa); qa = fmaf(d1, d1, qa); qa = fmaf(d2, d2, qa); qa = fmaf(d3, d3, qa);
-    qb = fmaf(e0, e0, qb); qb = fmaf(e1, e1, qb); qb = fmaf(e2, e2, qb); qb = fmaf(e3, e3, qb);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    qa += __shfl_xor_sync(0xffffffffu, qa, o);
-    qb += __shfl_xor_sync(0xffffffffu, qb, o);
-  }
-  rstd_a = rsqrtf(qa * inv_d + eps);
-  rstd_b = rsqrtf(qb * inv_d + eps);
+  lo = pack2u(v.x << 16, v.x & 0xFFFF0000u);
+  hi = pack2u(v.y << 16, v.y & 0xFFFF0000u);
 }
 
 template <typename TX>
-__device__ __forceinline__ void ln_row_stats(const TX* xr, int nquad, int lane, float inv_d, float eps, float& mean,
-                                             float& rstd) {
-  float sum = 0.f;
-#pragma unroll 8
-  for (int q = lane; q < nquad; q += 32) {
-    const float4 v = ld_quad<TX>(xr, q);
-    sum += (v.x + v.y) + (v.z + v.w);
-  }
-  mean = warp_sum(sum) * inv_d;
-  float sq = 0.f;
-#pragma unroll 8
-  for (int q = lane; q < nquad; q += 32) {
-    const float4 v = ld_quad<TX>(xr, q);
-    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-    sq = fmaf(d0, d0, sq); sq = fmaf(d1, d1, sq); sq = fmaf(d2, d2, sq); sq = fmaf(d3, d3, sq);
-  }
-  rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
-}
-
-__device__ __forceinline__ uint2 ln_out_quad(const float4& v, float mean, float rstd, const uint2& wq, const uint2& bq,
-                                             const float4& sc, const float4& sh) {
-  const float y0 = fmaf((v.x - mean) * rstd, bf16_lo(wq.x), bf16_lo(bq.x));
-  const float y1 = fmaf((v.y - mean) * rstd, bf16_hi(wq.x), bf16_hi(bq.x));
-  const float y2 = fmaf((v.z - mean) * rstd, bf16_lo(wq.y), bf16_lo(bq.y));
-  const float y3 = fmaf((v.w - mean) * rstd, bf16_hi(wq.y), bf16_hi(bq.y));
-  uint2 o;
-  o.x = pack_bf16x2(fmaf(y0, 1.0f + sc.x, sh.x), fmaf(y1, 1.0f + sc.y, sh.y));
-  o.y = pack_bf16x2(fmaf(y2, 1.0f + sc.z, sh.z), fmaf(y3, 1.0f + sc.w, sh.w));
-  return o;
-}
-
-template <typename TX>
-__global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_bulk_kernel(
+__global__ void __launch_bounds__(LnCfg<TX>::kWarps * 32) ln_modulate_bulk_kernel(
     const TX* __restrict__ x, bf16* __restrict__ out, const bf16* __restrict__ w, const bf16* __restrict__ b, float eps,
     const float* __restrict__ shift_img, const float* __restrict__ scale_img, const float* __restrict__ shift_txt,
     const float* __restrict__ scale_txt, int64_t mod_stride, int rows, int rows_per_batch, int tok_offset, int text_len,
     int D, int rows_per_warp) {
+  constexpr int kWarps = LnCfg<TX>::kWarps;
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t row_bytes = (uint32_t)D * sizeof(TX);
-  uint8_t* ring = ln_smem + (size_t)warp * kLnStages * row_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)kLnWarps * kLnStages * row_bytes) + warp * kLnStages;
+  float* tabs = reinterpret_cast<float*>(ln_smem);                       // [combo 0 | 1][A | C][D]
+  uint8_t* ring = ln_smem + (size_t)4 * D * sizeof(float) + (size_t)warp * kLnStages * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)4 * D * sizeof(float) + (size_t)kWarps * kLnStages * row_bytes) +
+                   warp * kLnStages;
   const int nquad = D >> 2;
-  const int64_t r0 = (int64_t)(blockIdx.x * kLnWarps + warp) * rows_per_warp;
+  const int64_t r0 = (int64_t)(blockIdx.x * kWarps + warp) * rows_per_warp;
   const int64_t r1 = min((int64_t)rows, r0 + rows_per_warp);
   if (lane == 0) {
     for (int s = 0; s < kLnStages; ++s) mbar_init(&bars[s], 1);
@@ -186,15 +134,36 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_bulk_kernel(
       }
     }
   }
-  __syncwarp();
-  const float inv_d = 1.0f / (float)D;
-  auto segment = [&](int64_t row, const float4*& shift, const float4*& scale) {
+  // (sample, segment) combination of a row: 2 * sample + is_text
+  auto combo_of = [&](int64_t row) {
     const int bidx = (int)(row / rows_per_batch);
     const int t = (int)(row - (int64_t)bidx * rows_per_batch);
-    const bool is_text = (tok_offset + t) < text_len;
-    shift = reinterpret_cast<const float4*>((is_text ? shift_txt : shift_img) + (int64_t)bidx * mod_stride);
-    scale = reinterpret_cast<const float4*>((is_text ? scale_txt : scale_img) + (int64_t)bidx * mod_stride);
+    return 2 * bidx + (((tok_offset + t) < text_len) ? 1 : 0);
   };
+  auto mod_ptrs = [&](int combo, const float*& sh, const float*& sc) {
+    const bool is_text = combo & 1;
+    sh = (is_text ? shift_txt : shift_img) + (int64_t)(combo >> 1) * mod_stride;
+    sc = (is_text ? scale_txt : scale_img) + (int64_t)(combo >> 1) * mod_stride;
+  };
+  // the CTA's rows are contiguous: tables for the combinations of its first and of its last row
+  const int64_t b0 = (int64_t)blockIdx.x * kWarps * rows_per_warp;
+  const int64_t b1 = min((int64_t)rows, b0 + (int64_t)kWarps * rows_per_warp) - 1;
+  const int combo0 = combo_of(b0), combo1 = combo_of(b1 > b0 ? b1 : b0);
+  for (int c = 0; c < 2; ++c) {
+    if (c == 1 && combo1 == combo0) break;
+    const float *sh, *sc;
+    mod_ptrs(c == 0 ? combo0 : combo1, sh, sc);
+    float* A = tabs + (size_t)c * 2 * D;
+    float* C = A + D;
+    for (int e = threadIdx.x; e < D; e += blockDim.x) {
+      const float wv = __bfloat162float(w[e]), bv = __bfloat162float(b[e]);
+      const float one_sc = 1.0f + sc[e];
+      A[e] = wv * one_sc;
+      C[e] = fmaf(bv, one_sc, sh[e]);
+    }
+  }
+  __syncthreads();
+  const float inv_d = 1.0f / (float)D;
   auto refill = [&](int it, int64_t row_done) {   // stage (it % kLnStages) has been read by every lane
     const int64_t nxt = row_done + kLnStages;
     if (lane == 0 && nxt < r1) {
@@ -204,53 +173,88 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_modulate_bulk_kernel(
       bulk_load_1d(ring + s * row_bytes, x + nxt * D, row_bytes, &bars[s]);
     }
   };
+  constexpr int KQ = 16;   // quads per lane: D <= 32 * 4 * 16 = 2048
   int it = 0;
-  int64_t row = r0;
-  while (row < r1) {
-    const int sa = it % kLnStages;
-    const TX* xa = reinterpret_cast<const TX*>(ring + sa * row_bytes);
-    const float4 *sh_a, *sc_a;
-    segment(row, sh_a, sc_a);
-    bool pair = row + 1 < r1;
-    const float4 *sh_b = sh_a, *sc_b = sc_a;
-    if (pair) {
-      segment(row + 1, sh_b, sc_b);
-      pair = (sh_b == sh_a) && (sc_b == sc_a);   // same sample and same text / image segment: the parameters are shared
+  for (int64_t row = r0; row < r1; ++row, ++it) {
+    const int s = it % kLnStages;
+    mbar_wait(&bars[s], (it / kLnStages) & 1);
+    const TX* xr = reinterpret_cast<const TX*>(ring + s * row_bytes);
+    // the row moves from its ring stage into registers in one burst of independent loads; the stage is refilled at once
+    uint64_t xv[KQ][2];
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) {
+      const int q = lane + 32 * k;
+      if (q < nquad) ld_quad2<TX>(xr, q, xv[k][0], xv[k][1]);
+      else xv[k][0] = xv[k][1] = 0ull;
     }
-    mbar_wait(&bars[sa], (it / kLnStages) & 1);
-    if (pair) {
-      const int sb = (it + 1) % kLnStages;
-      mbar_wait(&bars[sb], ((it + 1) / kLnStages) & 1);
-      const TX* xb = reinterpret_cast<const TX*>(ring + sb * row_bytes);
-      float mean_a, rstd_a, mean_b, rstd_b;
-      ln_row_stats2<TX>(xa, xb, nquad, lane, inv_d, eps, mean_a, rstd_a, mean_b, rstd_b);
-      uint2* oa = reinterpret_cast<uint2*>(out + row * D);
-      uint2* ob = reinterpret_cast<uint2*>(out + (row + 1) * D);
-#pragma unroll 4
-      for (int q = lane; q < nquad; q += 32) {
-        const uint2 wq = __ldg(reinterpret_cast<const uint2*>(w) + q), bq = __ldg(reinterpret_cast<const uint2*>(b) + q);
-        const float4 sc = __ldg(sc_a + q), sh = __ldg(sh_a + q);
-        oa[q] = ln_out_quad(ld_quad<TX>(xa, q), mean_a, rstd_a, wq, bq, sc, sh);
-        ob[q] = ln_out_quad(ld_quad<TX>(xb, q), mean_b, rstd_b, wq, bq, sc, sh);
+    __syncwarp();
+    refill(it, row);
+    // mean
+    uint64_t acc = 0;   // (0.f, 0.f)
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) acc = add2(acc, add2(xv[k][0], xv[k][1]));
+    float s0, s1;
+    unpack2(acc, s0, s1);
+    const float mean = warp_sum(s0 + s1) * inv_d;
+    // variance (two-pass, like nn.LayerNorm); padding quads beyond D contribute (0 - mean)^2 and are subtracted exactly
+    const uint64_t nmean2 = pack2(-mean, -mean);
+    acc = 0;
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) {
+      if (lane + 32 * k < nquad) {
+        const uint64_t lo = add2(xv[k][0], nmean2), hi = add2(xv[k][1], nmean2);
+        acc = fma2(lo, lo, acc);
+        acc = fma2(hi, hi, acc);
       }
-      __syncwarp();
-      refill(it, row);
-      refill(it + 1, row + 1);
-      it += 2;
-      row += 2;
+    }
+    unpack2(acc, s0, s1);
+    const float rstd = rsqrtf(warp_sum(s0 + s1) * inv_d + eps);
+    const int combo = combo_of(row);
+    uint2* orow = reinterpret_cast<uint2*>(out + row * D);
+    if (combo == combo0 || combo == combo1) {
+      const ulonglong2* A = reinterpret_cast<const ulonglong2*>(tabs + (size_t)(combo == combo0 ? 0 : 1) * 2 * D);
+      const ulonglong2* C = A + (D >> 2);
+      const uint64_t g2 = pack2(rstd, rstd), h2 = pack2(-mean * rstd, -mean * rstd);
+#pragma unroll
+      for (int k = 0; k < KQ; ++k) {
+        const int q = lane + 32 * k;
+        if (q < nquad) {
+          const ulonglong2 a = A[q], c = C[q];
+          const uint64_t lo = fma2(fma2(xv[k][0], g2, h2), a.x, c.x);
+          const uint64_t hi = fma2(fma2(xv[k][1], g2, h2), a.y, c.y);
+          float y0, y1, y2, y3;
+          unpack2(lo, y0, y1);
+          unpack2(hi, y2, y3);
+          uint2 o;
+          o.x = pack_bf16x2(y0, y1);
+          o.y = pack_bf16x2(y2, y3);
+          orow[q] = o;
+        }
+      }
     } else {
-      float mean_a, rstd_a;
-      ln_row_stats<TX>(xa, nquad, lane, inv_d, eps, mean_a, rstd_a);
-      uint2* oa = reinterpret_cast<uint2*>(out + row * D);
-#pragma unroll 4
-      for (int q = lane; q < nquad; q += 32) {
-        const uint2 wq = __ldg(reinterpret_cast<const uint2*>(w) + q), bq = __ldg(reinterpret_cast<const uint2*>(b) + q);
-        oa[q] = ln_out_quad(ld_quad<TX>(xa, q), mean_a, rstd_a, wq, bq, __ldg(sc_a + q), __ldg(sh_a + q));
+      // a third (sample, segment) combination inside one CTA's row range (tiny shapes): parameters from global memory
+      const float *sh, *sc;
+      mod_ptrs(combo, sh, sc);
+#pragma unroll
+      for (int k = 0; k < KQ; ++k) {
+        const int q = lane + 32 * k;
+        if (q < nquad) {
+          float v[4];
+          unpack2(xv[k][0], v[0], v[1]);
+          unpack2(xv[k][1], v[2], v[3]);
+          float y[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int idx = 4 * q + e;
+            const float t = fmaf((v[e] - mean) * rstd, __bfloat162float(w[idx]), __bfloat162float(b[idx]));
+            y[e] = fmaf(t, 1.0f + sc[idx], sh[idx]);
+          }
+          uint2 o;
+          o.x = pack_bf16x2(y[0], y[1]);
+          o.y = pack_bf16x2(y[2], y[3]);
+          orow[q] = o;
+        }
       }
-      __syncwarp();
-      refill(it, row);
-      it += 1;
-      row += 1;
     }
   }
 }
@@ -566,36 +570,35 @@ extern "C" int ld_layernorm_modulate(const void* x, int x_is_f32, void* out, con
   const int rows = batch * rows_per_batch;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t esz = x_is_f32 ? 4 : 2;
-  const size_t smem = (size_t)kLnWarps * kLnStages * D * esz + kLnWarps * kLnStages * 8;
+  const int ln_warps = x_is_f32 ? LnCfg<float>::kWarps : LnCfg<bf16>::kWarps;
+  const size_t smem = (size_t)4 * D * sizeof(float) + (size_t)ln_warps * kLnStages * D * esz + (size_t)ln_warps * kLnStages * 8;
   // the bulk-copy version needs 16-byte row granularity and its ring in shared memory; mod vectors must be 16-byte aligned
-  const bool aligned = ((D * esz) % 16 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (mod_batch_stride % 4 == 0) &&
-                       ((reinterpret_cast<uintptr_t>(shift_img) | reinterpret_cast<uintptr_t>(scale_img) |
-                         reinterpret_cast<uintptr_t>(shift_txt) | reinterpret_cast<uintptr_t>(scale_txt)) % 16 == 0) &&
-                       ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) % 8 == 0);
-  if (aligned && smem <= 200 * 1024) {
+  const bool aligned = ((D * esz) % 16 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (D % 4 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(out)) % 8 == 0);
+  if (aligned && smem <= 220 * 1024) {
     static bool attr_set[64][2] = {};
     int dev = 0;
     LD_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_set[dev][x_is_f32 ? 1 : 0]) {
       if (x_is_f32)
-        LD_CHECK_CUDA(cudaFuncSetAttribute(ln_modulate_bulk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        LD_CHECK_CUDA(cudaFuncSetAttribute(ln_modulate_bulk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       else
-        LD_CHECK_CUDA(cudaFuncSetAttribute(ln_modulate_bulk_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        LD_CHECK_CUDA(cudaFuncSetAttribute(ln_modulate_bulk_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       attr_set[dev][x_is_f32 ? 1 : 0] = true;
     }
     const int blocks_per_sm = smem <= 100 * 1024 ? 2 : 1;
-    // every warp owns a contiguous range of rows (so the two rows of a pair share their parameters almost always)
-    const int max_warps = sm_count() * blocks_per_sm * kLnWarps;
+    // every warp owns a contiguous range of rows, every CTA therefore too (its parameter tables cover it)
+    const int max_warps = sm_count() * blocks_per_sm * ln_warps;
     int rows_per_warp = (rows + max_warps - 1) / max_warps;
-    if (rows_per_warp < 2) rows_per_warp = 2;
-    const int grid = (rows + rows_per_warp * kLnWarps - 1) / (rows_per_warp * kLnWarps);
+    if (rows_per_warp < 1) rows_per_warp = 1;
+    const int grid = (rows + rows_per_warp * ln_warps - 1) / (rows_per_warp * ln_warps);
     if (x_is_f32)
-      ln_modulate_bulk_kernel<float><<<grid, kLnWarps * 32, smem, st>>>((const float*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
+      ln_modulate_bulk_kernel<float><<<grid, ln_warps * 32, smem, st>>>((const float*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
                                                                          eps, shift_img, scale_img, shift_txt, scale_txt,
                                                                          mod_batch_stride, rows, rows_per_batch, tok_offset,
                                                                          text_len, D, rows_per_warp);
     else
-      ln_modulate_bulk_kernel<bf16><<<grid, kLnWarps * 32, smem, st>>>((const bf16*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
+      ln_modulate_bulk_kernel<bf16><<<grid, ln_warps * 32, smem, st>>>((const bf16*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
                                                                         eps, shift_img, scale_img, shift_txt, scale_txt,
                                                                         mod_batch_stride, rows, rows_per_batch, tok_offset,
                                                                         text_len, D, rows_per_warp);

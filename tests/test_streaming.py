@@ -119,3 +119,47 @@ def test_streaming_against_oracle_sampler():
         assert torch.equal(chunks[k][:, :2], chunks[k - 1][:, 2:])
     r = ((out.float().cpu().double() - ref.double()).norm() / ref.double().norm()).item()
     assert r <= 2e-2, f"streamed latent rel-L2 {r:.3e} vs the oracle loop"
+
+
+@pytest.mark.gpu
+def test_full_shape_stream_chunks_against_oracle_sampler():
+    """BASELINE config 5 at the FULL latent shape (13 x 16 x 60 x 90 per chunk, 7-latent-frame fixed prefix, 50 steps per
+    chunk, 3 chained chunks): the streaming driver + fused sampler update on the GPU against the oracle sampler loop on the
+    CPU, same noise stream.  The network is the analytic stand-in the reference-generated sampler golden uses
+    (oracle/make_golden.py: timestep-, conditioning- and batch-row-dependent, bf16 output) so that the CPU side finishes in
+    seconds; the network itself is checked at this shape by test_full_shape_step_against_oracle_fp32_on_gpu."""
+    from landiff_b200.sampling import VPSDEDPMPP2MSampler
+    from oracle import dit_oracle as O
+    from oracle.make_golden import toy_network
+
+    plan = S.StreamPlan(n_chunks=3, chunk_frames=13, prefix_frames=7)
+    C, H, W = 16, 60, 90
+    g = torch.Generator().manual_seed(4)
+    ctx = torch.randn(1, 8, 16, generator=g)
+    feats = [torch.zeros(1, 13, C, H, W) for _ in range(3)]       # the stand-in network does not read the registry
+
+    gen = torch.Generator().manual_seed(9)
+    pieces, prefix = [], None
+    for k in range(3):
+        x0 = torch.randn(1, 13, C, H, W, generator=gen)
+        if prefix is not None:
+            x0 = torch.cat([prefix, x0[:, 7:]], dim=1)
+        smp = O.OracleSampler(num_steps=50, fixed_frames=0 if prefix is None else 7)
+        z = smp(lambda x2, t2, c2: toy_network(x2, t2, {"crossattn": c2}), x0, ctx, torch.zeros_like(ctx), gen)
+        pieces.append(z if k == 0 else z[:, 7:])
+        prefix = z[:, 6:].clone()
+    ref = torch.cat(pieces, dim=1)
+
+    gen2 = torch.Generator().manual_seed(9)
+    noise = lambda t: torch.randn(t.shape, generator=gen2).to(t.device)
+    chunks = {}
+    out = S.sample_stream(toy_network, lambda ff: VPSDEDPMPP2MSampler(num_steps=50, device="cuda", fixed_frames=ff), plan,
+                          (C, H, W), {"crossattn": ctx.cuda()}, {"crossattn": torch.zeros_like(ctx).cuda()}, feats,
+                          lambda f: None, device="cuda", noise_fn=noise,
+                          chunk_callback=lambda k, z: chunks.__setitem__(k, z.float().cpu().clone()))
+    torch.cuda.synchronize()
+    assert out.shape == (1, plan.total_frames, C, H, W) == (1, 25, 16, 60, 90)
+    for k in (1, 2):   # the fixed prefix of chunk k+1 is bit-identical to the last 7 latent frames of chunk k
+        assert torch.equal(chunks[k][:, :7], chunks[k - 1][:, 6:])
+    r = ((out.float().cpu().double() - ref.double()).norm() / ref.double().norm()).item()
+    assert r <= 5e-3, f"full-shape streamed latent rel-L2 {r:.3e} vs the oracle sampler loop"

@@ -117,6 +117,10 @@ def main():
         ms = timeit(lambda: ops.layernorm_modulate(x, w, b, 1e-5, mod[:, 0], mod[:, 1], mod[:, 6], mod[:, 7], 12 * D, B, N, 0, TL, out=out), a.iters)
         gb = 2 * M * D * 2 / 1e9
         print(f"  layernorm_modulate: {ms:8.3f} ms  {gb / ms * 1e3:7.1f} GB/s  {gb / ms * 1e3 / bw_peak:.3f} of {how} peak", flush=True)
+        xf = x.float()
+        ms = timeit(lambda: ops.layernorm_modulate(xf, w, b, 1e-5, mod[:, 0], mod[:, 1], mod[:, 6], mod[:, 7], 12 * D, B, N, 0, TL, out=out), a.iters)
+        gb = M * D * (4 + 2) / 1e9
+        print(f"  layernorm_modulate (fp32 residual stream in): {ms:8.3f} ms  {gb / ms * 1e3:7.1f} GB/s  {gb / ms * 1e3 / bw_peak:.3f} of {how} peak", flush=True)
         xl = torch.randn(1, 13, 16, 60, 90, device=dev)
         nu = torch.randn(1, 13, 16, 60, 90, device=dev).bfloat16()
         n = xl.numel()
