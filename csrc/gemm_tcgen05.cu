@@ -118,6 +118,11 @@ __device__ __forceinline__ void epi_fetch(const ld_gemm_args& p, const RowCtx& r
 #pragma unroll
     for (int g = 0; g < 8; ++g) o.gate[g] = gt[g];
   }
+  if constexpr (EPI == LD_EPI_BIAS_ADD) {
+    const uint4* a2 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.add2) + rc.out_row * p.ld_out + col);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) o.add2[g] = a2[g];
+  }
   if constexpr (EPI == LD_EPI_BIAS_POS) {
     const uint4* ps = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.pos) +
                                                      (int64_t)(p.tok_offset + rc.t) * p.N + col);
@@ -148,10 +153,19 @@ __device__ __forceinline__ void epilogue32(const ld_gemm_args& p, const RowCtx& 
     }
   }
 
-  if constexpr (EPI == LD_EPI_NONE || EPI == LD_EPI_BIAS || EPI == LD_EPI_BIAS_GELU) {
+  if constexpr (EPI == LD_EPI_NONE || EPI == LD_EPI_BIAS || EPI == LD_EPI_BIAS_GELU || EPI == LD_EPI_BIAS_ADD) {
     if constexpr (EPI == LD_EPI_BIAS_GELU) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) acc[i] = gelu_tanh(acc[i]);
+    }
+    if constexpr (EPI == LD_EPI_BIAS_ADD) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float av[8];
+        unpack8_u4(o.add2[g], av);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[g * 8 + i] += av[i];
+      }
     }
     bf16* op = reinterpret_cast<bf16*>(p.out) + rc.out_row * p.ld_out + col;
 #pragma unroll
@@ -718,6 +732,9 @@ extern "C" int ld_gemm_bf16(const ld_gemm_args* args, void* stream) {
     case LD_EPI_NONE: return dispatch_bn<LD_EPI_NONE>(a, st);
     case LD_EPI_BIAS: return dispatch_bn<LD_EPI_BIAS>(a, st);
     case LD_EPI_BIAS_GELU: return dispatch_bn<LD_EPI_BIAS_GELU>(a, st);
+    case LD_EPI_BIAS_ADD:
+      LD_CHECK_ARG(a.add2 != nullptr, "ld_gemm_bf16: BIAS_ADD needs add2");
+      return dispatch_bn<LD_EPI_BIAS_ADD>(a, st);
     case LD_EPI_GATED_RESID:
       LD_CHECK_ARG(a.resid && a.gate_img && a.gate_txt, "ld_gemm_bf16: GATED_RESID needs resid and gates");
       return dispatch_bn<LD_EPI_GATED_RESID>(a, st);

@@ -82,14 +82,22 @@ __device__ __forceinline__ void row_stats(const float (*vals)[8], int nvec, int 
 //     lane, mbarrier complete_tx): rows in flight do not depend on what the warp is doing.
 // Quads of 4 elements per lane and step: conflict-free 16-byte (fp32) / 8-byte (bf16) shared-memory reads, 8-byte coalesced
 // stores.
-constexpr int kLnStages = 4;
-
-template <typename TX>
+// Configuration of the bulk LayerNorm-modulate kernel.  KQX = 0: any D <= 2048 (16 predicated quads per lane); KQX > 0: D is
+// exactly 128 * KQX (1920 -> 15), the per-quad bounds checks and their branches compile away.
+template <typename TX, int KQX>
 struct LnCfg;
 template <>
-struct LnCfg<float> { static constexpr int kWarps = 6; };     // 6 x 4 x 7.5 KB rows + 30 KB tables = 210 KB
+struct LnCfg<float, 0> { static constexpr int kWarps = 6, kStages = 4; };    // 6 x 4 x 7.5 KB rows + 30 KB tables = 210 KB
 template <>
-struct LnCfg<bf16> { static constexpr int kWarps = 12; };     // 12 x 4 x 3.75 KB rows + 30 KB tables = 210 KB
+struct LnCfg<bf16, 0> { static constexpr int kWarps = 12, kStages = 4; };    // 12 x 4 x 3.75 KB rows + 30 KB tables = 210 KB
+template <>
+struct LnCfg<float, 15> { static constexpr int kWarps = 8, kStages = 3; };   // 8 x 3 x 7.5 KB + 30 KB = 210 KB
+template <>
+struct LnCfg<bf16, 15> { static constexpr int kWarps = 16, kStages = 3; };   // 16 x 3 x 3.75 KB + 30 KB = 210 KB
+template <>
+struct LnCfg<float, 115> { static constexpr int kWarps = 6, kStages = 4; };  // 1xx: the same exact-D code at the generic
+template <>
+struct LnCfg<bf16, 115> { static constexpr int kWarps = 12, kStages = 4; };  // kernel's warp / stage split (A/B switch)
 
 template <typename TX>
 __device__ __forceinline__ void ld_quad2(const TX* row, int q, uint64_t& lo, uint64_t& hi);
@@ -106,13 +114,15 @@ __device__ __forceinline__ void ld_quad2<bf16>(const bf16* row, int q, uint64_t&
   hi = pack2u(v.y << 16, v.y & 0xFFFF0000u);
 }
 
-template <typename TX>
-__global__ void __launch_bounds__(LnCfg<TX>::kWarps * 32) ln_modulate_bulk_kernel(
+template <typename TX, int KQX>
+__global__ void __launch_bounds__(LnCfg<TX, KQX>::kWarps * 32) ln_modulate_bulk_kernel(
     const TX* __restrict__ x, bf16* __restrict__ out, const bf16* __restrict__ w, const bf16* __restrict__ b, float eps,
     const float* __restrict__ shift_img, const float* __restrict__ scale_img, const float* __restrict__ shift_txt,
     const float* __restrict__ scale_txt, int64_t mod_stride, int rows, int rows_per_batch, int tok_offset, int text_len,
-    int D, int rows_per_warp) {
-  constexpr int kWarps = LnCfg<TX>::kWarps;
+    int D) {
+  constexpr int kWarps = LnCfg<TX, KQX>::kWarps;
+  constexpr int kLnStages = LnCfg<TX, KQX>::kStages;
+  constexpr bool kExact = KQX > 0;
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -122,8 +132,11 @@ __global__ void __launch_bounds__(LnCfg<TX>::kWarps * 32) ln_modulate_bulk_kerne
   uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)4 * D * sizeof(float) + (size_t)kWarps * kLnStages * row_bytes) +
                    warp * kLnStages;
   const int nquad = D >> 2;
-  const int64_t r0 = (int64_t)(blockIdx.x * kWarps + warp) * rows_per_warp;
-  const int64_t r1 = min((int64_t)rows, r0 + rows_per_warp);
+  // balanced contiguous split: CTA c owns rows [rows*c/G, rows*(c+1)/G), warp w the same fraction of the CTA's range
+  const int64_t b0 = (int64_t)rows * blockIdx.x / gridDim.x;
+  const int64_t bn = (int64_t)rows * (blockIdx.x + 1) / gridDim.x - b0;
+  const int64_t r0 = b0 + bn * warp / kWarps;
+  const int64_t r1 = b0 + bn * (warp + 1) / kWarps;
   if (lane == 0) {
     for (int s = 0; s < kLnStages; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
@@ -146,8 +159,7 @@ __global__ void __launch_bounds__(LnCfg<TX>::kWarps * 32) ln_modulate_bulk_kerne
     sc = (is_text ? scale_txt : scale_img) + (int64_t)(combo >> 1) * mod_stride;
   };
   // the CTA's rows are contiguous: tables for the combinations of its first and of its last row
-  const int64_t b0 = (int64_t)blockIdx.x * kWarps * rows_per_warp;
-  const int64_t b1 = min((int64_t)rows, b0 + (int64_t)kWarps * rows_per_warp) - 1;
+  const int64_t b1 = b0 + bn - 1;
   const int combo0 = combo_of(b0), combo1 = combo_of(b1 > b0 ? b1 : b0);
   for (int c = 0; c < 2; ++c) {
     if (c == 1 && combo1 == combo0) break;
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(LnCfg<TX>::kWarps * 32) ln_modulate_bulk_kerne
       bulk_load_1d(ring + s * row_bytes, x + nxt * D, row_bytes, &bars[s]);
     }
   };
-  constexpr int KQ = 16;   // quads per lane: D <= 32 * 4 * 16 = 2048
+  constexpr int KQ = kExact ? (KQX % 100) : 16;   // quads per lane: D <= 32 * 4 * 16 = 2048, or exactly 128 * KQ
   int it = 0;
   for (int64_t row = r0; row < r1; ++row, ++it) {
     const int s = it % kLnStages;
@@ -184,7 +196,7 @@ __global__ void __launch_bounds__(LnCfg<TX>::kWarps * 32) ln_modulate_bulk_kerne
 #pragma unroll
     for (int k = 0; k < KQ; ++k) {
       const int q = lane + 32 * k;
-      if (q < nquad) ld_quad2<TX>(xr, q, xv[k][0], xv[k][1]);
+      if (kExact || q < nquad) ld_quad2<TX>(xr, q, xv[k][0], xv[k][1]);
       else xv[k][0] = xv[k][1] = 0ull;
     }
     __syncwarp();
@@ -201,7 +213,7 @@ __global__ void __launch_bounds__(LnCfg<TX>::kWarps * 32) ln_modulate_bulk_kerne
     acc = 0;
 #pragma unroll
     for (int k = 0; k < KQ; ++k) {
-      if (lane + 32 * k < nquad) {
+      if (kExact || lane + 32 * k < nquad) {
         const uint64_t lo = add2(xv[k][0], nmean2), hi = add2(xv[k][1], nmean2);
         acc = fma2(lo, lo, acc);
         acc = fma2(hi, hi, acc);
@@ -218,7 +230,7 @@ __global__ void __launch_bounds__(LnCfg<TX>::kWarps * 32) ln_modulate_bulk_kerne
 #pragma unroll
       for (int k = 0; k < KQ; ++k) {
         const int q = lane + 32 * k;
-        if (q < nquad) {
+        if (kExact || q < nquad) {
           const ulonglong2 a = A[q], c = C[q];
           const uint64_t lo = fma2(fma2(xv[k][0], g2, h2), a.x, c.x);
           const uint64_t hi = fma2(fma2(xv[k][1], g2, h2), a.y, c.y);
@@ -238,7 +250,7 @@ __global__ void __launch_bounds__(LnCfg<TX>::kWarps * 32) ln_modulate_bulk_kerne
 #pragma unroll
       for (int k = 0; k < KQ; ++k) {
         const int q = lane + 32 * k;
-        if (q < nquad) {
+        if (kExact || q < nquad) {
           float v[4];
           unpack2(xv[k][0], v[0], v[1]);
           unpack2(xv[k][1], v[2], v[3]);
@@ -570,38 +582,50 @@ extern "C" int ld_layernorm_modulate(const void* x, int x_is_f32, void* out, con
   const int rows = batch * rows_per_batch;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t esz = x_is_f32 ? 4 : 2;
-  const int ln_warps = x_is_f32 ? LnCfg<float>::kWarps : LnCfg<bf16>::kWarps;
-  const size_t smem = (size_t)4 * D * sizeof(float) + (size_t)ln_warps * kLnStages * D * esz + (size_t)ln_warps * kLnStages * 8;
+  // kernel flavour: exact-D instance for D = 1920 (the DiT width), generic otherwise; LD_LN_CFG=0 / 115 force the generic code /
+  // the exact code at the generic warp split (A/B switches for tools/kernel_bench.py)
+  static const int forced = [] { const char* e = getenv("LD_LN_CFG"); return e ? atoi(e) : -1; }();
+  int kqx = (D == 1920) ? 15 : 0;
+  if (forced == 0) kqx = 0;
+  if (forced == 115 && D == 1920) kqx = 115;
+  int ln_warps, ln_stages;
+  const void* kern;
+#define LD_LN_PICK(T, K)                                           \
+  do {                                                             \
+    ln_warps = LnCfg<T, K>::kWarps;                                \
+    ln_stages = LnCfg<T, K>::kStages;                              \
+    kern = (const void*)ln_modulate_bulk_kernel<T, K>;             \
+  } while (0)
+  if (x_is_f32) {
+    if (kqx == 15) LD_LN_PICK(float, 15); else if (kqx == 115) LD_LN_PICK(float, 115); else LD_LN_PICK(float, 0);
+  } else {
+    if (kqx == 15) LD_LN_PICK(bf16, 15); else if (kqx == 115) LD_LN_PICK(bf16, 115); else LD_LN_PICK(bf16, 0);
+  }
+#undef LD_LN_PICK
+  const size_t smem = (size_t)4 * D * sizeof(float) + (size_t)ln_warps * ln_stages * D * esz + (size_t)ln_warps * ln_stages * 8;
   // the bulk-copy version needs 16-byte row granularity and its ring in shared memory; mod vectors must be 16-byte aligned
   const bool aligned = ((D * esz) % 16 == 0) && (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (D % 4 == 0) &&
                        ((reinterpret_cast<uintptr_t>(out)) % 8 == 0);
   if (aligned && smem <= 220 * 1024) {
-    static bool attr_set[64][2] = {};
+    static bool attr_set[64][2][3] = {};
     int dev = 0;
     LD_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !attr_set[dev][x_is_f32 ? 1 : 0]) {
-      if (x_is_f32)
-        LD_CHECK_CUDA(cudaFuncSetAttribute(ln_modulate_bulk_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      else
-        LD_CHECK_CUDA(cudaFuncSetAttribute(ln_modulate_bulk_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      attr_set[dev][x_is_f32 ? 1 : 0] = true;
+    const int ki = kqx == 15 ? 1 : (kqx == 115 ? 2 : 0);
+    if (dev >= 0 && dev < 64 && !attr_set[dev][x_is_f32 ? 1 : 0][ki]) {
+      LD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      attr_set[dev][x_is_f32 ? 1 : 0][ki] = true;
     }
     const int blocks_per_sm = smem <= 100 * 1024 ? 2 : 1;
-    // every warp owns a contiguous range of rows, every CTA therefore too (its parameter tables cover it)
-    const int max_warps = sm_count() * blocks_per_sm * ln_warps;
-    int rows_per_warp = (rows + max_warps - 1) / max_warps;
-    if (rows_per_warp < 1) rows_per_warp = 1;
-    const int grid = (rows + rows_per_warp * ln_warps - 1) / (rows_per_warp * ln_warps);
-    if (x_is_f32)
-      ln_modulate_bulk_kernel<float><<<grid, ln_warps * 32, smem, st>>>((const float*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
-                                                                         eps, shift_img, scale_img, shift_txt, scale_txt,
-                                                                         mod_batch_stride, rows, rows_per_batch, tok_offset,
-                                                                         text_len, D, rows_per_warp);
-    else
-      ln_modulate_bulk_kernel<bf16><<<grid, ln_warps * 32, smem, st>>>((const bf16*)x, (bf16*)out, (const bf16*)w, (const bf16*)b,
-                                                                        eps, shift_img, scale_img, shift_txt, scale_txt,
-                                                                        mod_batch_stride, rows, rows_per_batch, tok_offset,
-                                                                        text_len, D, rows_per_warp);
+    // every warp owns a contiguous range of rows, every CTA therefore too (its parameter tables cover it); one CTA per SM
+    // (or two when they fit), rows split evenly over them inside the kernel
+    const int max_ctas = sm_count() * blocks_per_sm;
+    const int grid = rows < max_ctas ? rows : max_ctas;
+    int64_t mstride = mod_batch_stride;
+    int a_rows = rows, a_rpb = rows_per_batch, a_tok = tok_offset, a_tl = text_len, a_D = D;
+    void* args[] = {(void*)&x, (void*)&out, (void*)&w, (void*)&b, (void*)&eps, (void*)&shift_img, (void*)&scale_img,
+                    (void*)&shift_txt, (void*)&scale_txt, (void*)&mstride, (void*)&a_rows, (void*)&a_rpb, (void*)&a_tok,
+                    (void*)&a_tl, (void*)&a_D};
+    LD_CHECK_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(ln_warps * 32), args, smem, st));
     LD_CHECK_CUDA(cudaGetLastError());
     return LD_OK;
   }

@@ -42,7 +42,9 @@ enum ld_epilogue {
   LD_EPI_GATED_RESID = 3, /* out = resid + gate[seg]*(acc+bias) (+ add2)   :593-598, :619-624, :1357-1370       */
   LD_EPI_QKV = 4,         /* split Q|K|V, per-head LayerNorm(64) on Q,K, head-major store   :636-664 + SAT      */
   LD_EPI_BIAS_POS = 5,    /* out = acc + bias + pos[token]  patch-embed conv as GEMM :47-62, pos add :227-231   */
-  LD_EPI_UNPATCHIFY = 6   /* out[b,t,c,2h+p,2w+q] = acc + bias   final linear + unpatchify :392-410, :453-456   */
+  LD_EPI_UNPATCHIFY = 6,  /* out[b,t,c,2h+p,2w+q] = acc + bias   final linear + unpatchify :392-410, :453-456   */
+  LD_EPI_BIAS_ADD = 7     /* out = acc + bias + add2 (bf16, indexed like out)   ResnetBlock `x + h` of the semantic
+                             conditioner's conv decoder, semantic_models/modules/vq_gan_blocks.py:126-147           */
 };
 
 typedef struct ld_gemm_args {
@@ -181,6 +183,36 @@ int ld_sampler_update(const float* x, const void* net_u, const void* net_c, cons
                       const float* eps, float* x_out, float* den_out, int64_t n, float c_skip, float c_out,
                       float cfg, float m1, float m2, float m3, float m4, float mn, int mode, int net_is_f32,
                       void* stream);
+
+/* ---- semantic conditioner, upsample path ------------------------------------------------
+   The conv decoder between the semantic tokenizer's features and the control network's latent add
+   (landiff/diffusion/semantic_models/condition.py:86-137; modules/vq_gan_blocks.py:30-147, 480-606).  Activations are
+   channels-last bf16 [frames, H, W, C]; a 3x3 convolution = ld_im2col3x3 (GroupNorm + swish of the input applied on the
+   fly) + ld_gemm_bf16 with weights reordered to [Cout, (ky, kx, cin)] and epilogue LD_EPI_BIAS / LD_EPI_BIAS_ADD. */
+
+/* x [frames, C, P] (NCHW with P = H*W; bf16 or fp32) -> out [frames, P, C] bf16   (condition.py:104-107 input cast + layout) */
+int ld_nchw_to_nhwc(const void* x, int x_is_f32, void* out, int frames, int C, int P, void* stream);
+
+/* GroupNorm statistics (vq_gan_blocks.py:35-38: 32 groups, eps 1e-6) of channels-last frames x [frames, P, C] bf16:
+   stats [frames, groups, 2] fp32 = (mean, rstd), two passes (sum, then centred squares) reduced in a fixed order, so the
+   result is bit-reproducible.  scratch: fp32 [frames * ceil(P / 256) * groups]. */
+int ld_groupnorm_stats(const void* x, float* stats, float* scratch, int frames, int P, int C, int groups, float eps,
+                       void* stream);
+
+/* im2col of a 3x3 / stride 1 / padding 1 convolution: out [(frame, y, x), (ky, kx, c)] bf16.  gn_stats != NULL: the input is
+   first normalised with ld_groupnorm_stats' (mean, rstd), gamma/beta (bf16 [C]) and passed through swish when swish != 0
+   (norm -> nonlinearity -> conv, vq_gan_blocks.py:128-140, 599-604); padding taps are zeros of the ACTIVATED tensor. */
+int ld_im2col3x3(const void* x, void* out, int frames, int H, int W, int C, const float* gn_stats, const void* gamma,
+                 const void* beta, int groups, int swish, void* stream);
+
+/* torch.nn.PixelShuffle(2) on channels-last frames: x [frames, H, W, 4*C_out] -> out [frames, 2H, 2W, C_out]
+   (vq_gan_blocks.py:47-48, 63-64) */
+int ld_pixel_shuffle2(const void* x, void* out, int frames, int H, int W, int C_out, void* stream);
+
+/* direct 3x3 convolution to 16 channels: x channels-last [frames, H, W, Cin] bf16, w bf16 in torch layout [16, Cin, 3, 3],
+   bias bf16 [16] or NULL, out bf16 NCHW [frames, 16, H, W] — SemanticCond.conv_out, condition.py:49-56, 132-136 */
+int ld_conv3x3_to_nchw16(const void* x, const void* w, const void* bias, void* out, int frames, int H, int W, int Cin,
+                         void* stream);
 
 #ifdef __cplusplus
 }

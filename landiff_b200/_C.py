@@ -13,7 +13,7 @@ from . import build as _build
 
 LD_OK = 0
 
-EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_GATED_RESID, EPI_QKV, EPI_BIAS_POS, EPI_UNPATCHIFY = range(7)
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_GATED_RESID, EPI_QKV, EPI_BIAS_POS, EPI_UNPATCHIFY, EPI_BIAS_ADD = range(8)
 
 
 class GemmArgs(C.Structure):
@@ -55,6 +55,11 @@ SIGNATURES = {
     "ld_attention_shards_bf16": (C.c_int, [_vp, C.POINTER(KvShard), _i, _vp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
     "ld_attention_status": (C.c_int, [C.POINTER(C.c_uint), _i]),
     "ld_attention_merge": (C.c_int, [_fp, _fp, _fp, _fp, _vp, _i, _i, _i, _vp]),
+    "ld_nchw_to_nhwc": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _vp]),
+    "ld_groupnorm_stats": (C.c_int, [_vp, _fp, _fp, _i, _i, _i, _i, C.c_float, _vp]),
+    "ld_im2col3x3": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _fp, _vp, _vp, _i, _i, _vp]),
+    "ld_pixel_shuffle2": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "ld_conv3x3_to_nchw16": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ld_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
     "ld_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "ld_ipc_close": (C.c_int, [_vp]),
@@ -78,7 +83,7 @@ def lib_path() -> Path:
     return _build.LIB_PATH
 
 
-ABI_VERSION = 3   # must equal ld_abi_version() of the loaded library (bumped whenever a signature or struct changes)
+ABI_VERSION = 4   # must equal ld_abi_version() of the loaded library (bumped whenever a signature or struct changes)
 
 
 def load() -> C.CDLL:

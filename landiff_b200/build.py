@@ -17,7 +17,7 @@ ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / "csrc"
 LIB_DIR = ROOT / "landiff_b200" / "lib"
 LIB_PATH = LIB_DIR / "liblandiff_b200.so"
-SOURCES = ["abi.cu", "gemm_tcgen05.cu", "attn_tcgen05.cu", "row_kernels.cu", "peer_ring.cu"]
+SOURCES = ["abi.cu", "gemm_tcgen05.cu", "attn_tcgen05.cu", "row_kernels.cu", "peer_ring.cu", "conv_kernels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -479,8 +479,9 @@ class ControlDiffusionTransformer(DiffusionTransformer):
         kwargs.pop("semantic_video_frames", None)
         modules = kwargs.get("modules", {})
         super().__init__(*args, **kwargs)
-        # the semantic conditioner stays on reference code (out of scope); instantiate it only if given,
-        # with the keyword-only `dtype` the reference passes (dit_video_concat.py:926-928, condition.py:32-45)
+        # the semantic conditioner is whatever `semantic_condition_config` names — the reference SemanticCond, or the
+        # drop-in `landiff_b200.semantic.SemanticCond` (CUDA upsample path); it is instantiated
+        # only if given, with the keyword-only `dtype` the reference passes (dit_video_concat.py:926-928, condition.py:32-45)
         sc = modules.get("semantic_condition_config")
         self.semantic_conditioner = instantiate_from_config(sc, dtype=self.dtype) \
             if sc and sc.get("target") != "torch.nn.Identity" else nn.Identity()

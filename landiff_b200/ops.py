@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _C
-from ._C import (EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_POS, EPI_GATED_RESID, EPI_NONE, EPI_QKV, EPI_UNPATCHIFY,
+from ._C import (EPI_BIAS, EPI_BIAS_ADD, EPI_BIAS_GELU, EPI_BIAS_POS, EPI_GATED_RESID, EPI_NONE, EPI_QKV, EPI_UNPATCHIFY,
                  GemmArgs, check)
 
 BF16 = torch.bfloat16
@@ -119,6 +119,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epilogue: int, bias: Optional[torc
         if epilogue == EPI_BIAS_POS:
             _chk(pos, BF16, "pos")
             g.pos = pos.data_ptr()
+        if epilogue == EPI_BIAS_ADD:
+            _chk(add2, BF16, "add2")
+            if tuple(add2.shape) != tuple(out.shape) or not out.is_contiguous():
+                raise ValueError("gemm: BIAS_ADD needs a contiguous out and an add2 of the same shape")
+            g.add2 = add2.data_ptr()
     check(_C.load().ld_gemm_bf16(C.byref(g), _stream()), "ld_gemm_bf16")
     return ret
 
@@ -354,6 +359,117 @@ def sampler_update_f32(x, den_u, den_c, old_den, eps, *, cfg, m1=0.0, m2=0.0, m3
                           mode=mode, net_dtype=F32)
 
 
+# ---- semantic conditioner, upsample path (SURVEY.md section 8 row f2): channels-last conv stack ---------------------------
+def nchw_to_nhwc(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[F, C, H, W] bf16 / fp32 -> channels-last bf16 [F, H, W, C]."""
+    if x.dtype not in (BF16, F32):
+        raise TypeError(f"nchw_to_nhwc: x must be bf16 or fp32, got {x.dtype}")
+    _chk(x, x.dtype, "x")
+    if x.dim() != 4:
+        raise ValueError("nchw_to_nhwc: x must be [F, C, H, W]")
+    F_, C_, H, W = x.shape
+    if out is None:
+        out = torch.empty((F_, H, W, C_), dtype=BF16, device=x.device)
+    _chk(out, BF16, "out")
+    check(_C.load().ld_nchw_to_nhwc(x.data_ptr(), 1 if x.dtype == F32 else 0, out.data_ptr(), F_, C_, H * W, _stream()),
+          "ld_nchw_to_nhwc")
+    return out
+
+
+def groupnorm_stats(x: torch.Tensor, groups: int = 32, eps: float = 1e-6) -> torch.Tensor:
+    """x channels-last [F, H, W, C] bf16 -> fp32 [F, groups, 2] = (mean, rstd); two passes like torch, fixed reduction order."""
+    _chk(x, BF16, "x")
+    F_, H, W, C_ = x.shape
+    stats = torch.empty((F_, groups, 2), dtype=F32, device=x.device)
+    scratch = torch.empty((F_ * ((H * W + 255) // 256) * groups,), dtype=F32, device=x.device)
+    check(_C.load().ld_groupnorm_stats(x.data_ptr(), stats.data_ptr(), scratch.data_ptr(), F_, H * W, C_, groups, float(eps),
+                                       _stream()), "ld_groupnorm_stats")
+    return stats
+
+
+def im2col3x3(x: torch.Tensor, out: Optional[torch.Tensor] = None, *, gn=None, swish: bool = True) -> torch.Tensor:
+    """x channels-last [F, H, W, C] bf16 -> [F*H*W, 9*C] bf16 (taps-major).  gn = (stats, gamma, beta, groups) applies
+    GroupNorm (+ swish) to the input on the fly."""
+    _chk(x, BF16, "x")
+    F_, H, W, C_ = x.shape
+    if out is None:
+        out = torch.empty((F_ * H * W, 9 * C_), dtype=BF16, device=x.device)
+    _chk(out, BF16, "out")
+    if out.numel() != F_ * H * W * 9 * C_:
+        raise ValueError("im2col3x3: out has the wrong size")
+    if gn is None:
+        st = gm = gb = None
+        groups = 0
+    else:
+        st, gm, gb, groups = gn
+        _chk(st, F32, "gn stats"); _chk(gm, BF16, "gamma"); _chk(gb, BF16, "beta")
+        if st.numel() != F_ * groups * 2 or gm.numel() != C_ or gb.numel() != C_:
+            raise ValueError("im2col3x3: GroupNorm operand sizes")
+    check(_C.load().ld_im2col3x3(x.data_ptr(), out.data_ptr(), F_, H, W, C_, _ptr(st), _ptr(gm), _ptr(gb), int(groups),
+                                 1 if swish else 0, _stream()), "ld_im2col3x3")
+    return out
+
+
+def pixel_shuffle2(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """torch.nn.PixelShuffle(2) on channels-last frames: [F, H, W, 4*Co] -> [F, 2H, 2W, Co]."""
+    _chk(x, BF16, "x")
+    F_, H, W, C4 = x.shape
+    if C4 % 4:
+        raise ValueError("pixel_shuffle2: channels must be a multiple of 4")
+    if out is None:
+        out = torch.empty((F_, 2 * H, 2 * W, C4 // 4), dtype=BF16, device=x.device)
+    _chk(out, BF16, "out")
+    check(_C.load().ld_pixel_shuffle2(x.data_ptr(), out.data_ptr(), F_, H, W, C4 // 4, _stream()), "ld_pixel_shuffle2")
+    return out
+
+
+def conv3x3_to_nchw16(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None):
+    """3x3 / padding 1 convolution to 16 channels: x channels-last [F, H, W, Cin], w [16, Cin, 3, 3] (torch layout) ->
+    NCHW bf16 [F, 16, H, W]."""
+    _chk(x, BF16, "x"); _chk(w, BF16, "w")
+    F_, H, W, Cin = x.shape
+    if tuple(w.shape) != (16, Cin, 3, 3):
+        raise ValueError(f"conv3x3_to_nchw16: w must be [16, {Cin}, 3, 3], got {tuple(w.shape)}")
+    if bias is not None:
+        _chk(bias, BF16, "bias")
+    if out is None:
+        out = torch.empty((F_, 16, H, W), dtype=BF16, device=x.device)
+    _chk(out, BF16, "out")
+    check(_C.load().ld_conv3x3_to_nchw16(x.data_ptr(), w.data_ptr(), _ptr(bias), out.data_ptr(), F_, H, W, Cin, _stream()),
+          "ld_conv3x3_to_nchw16")
+    return out
+
+
+def conv3x3(x: torch.Tensor, w_taps: torch.Tensor, bias: Optional[torch.Tensor], *, gn=None, swish: bool = True,
+            add: Optional[torch.Tensor] = None, col: Optional[torch.Tensor] = None, max_col_bytes: int = 256 << 20):
+    """3x3 / stride 1 / padding 1 convolution on channels-last frames as im2col + tcgen05 GEMM.  w_taps: [Cout, 9*Cin] bf16
+    in (ky, kx, cin) order (`conv_weight_taps`); gn / swish: see im2col3x3; add: residual [F, H, W, Cout] added in the GEMM
+    epilogue.  Frames are processed in chunks so that the im2col buffer stays under max_col_bytes."""
+    _chk(x, BF16, "x")
+    F_, H, W, Cin = x.shape
+    Cout = w_taps.shape[0]
+    out = torch.empty((F_, H, W, Cout), dtype=BF16, device=x.device)
+    per_frame = H * W * 9 * Cin * 2
+    chunk = max(1, min(F_, max_col_bytes // per_frame))
+    if col is None or col.numel() < chunk * H * W * 9 * Cin:
+        col = torch.empty((chunk * H * W * 9 * Cin,), dtype=BF16, device=x.device)
+    for f0 in range(0, F_, chunk):
+        f1 = min(F_, f0 + chunk)
+        g = None if gn is None else (gn[0][f0:f1], gn[1], gn[2], gn[3])
+        a = im2col3x3(x[f0:f1], col[: (f1 - f0) * H * W * 9 * Cin].view((f1 - f0) * H * W, 9 * Cin), gn=g, swish=swish)
+        o = out[f0:f1].view(-1, Cout)
+        if add is None:
+            gemm(a, w_taps, epilogue=EPI_BIAS, bias=bias, out=o)
+        else:
+            gemm(a, w_taps, epilogue=EPI_BIAS_ADD, bias=bias, out=o, add2=add[f0:f1].view(-1, Cout))
+    return out
+
+
+def conv_weight_taps(w: torch.Tensor) -> torch.Tensor:
+    """torch conv weight [Cout, Cin, 3, 3] -> the GEMM operand [Cout, (ky, kx, cin)] (one-time layout change at load)."""
+    return w.detach().permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
 _registered = False
 
 
@@ -389,6 +505,20 @@ def register_torch_ops() -> None:
     D("timestep_embedding(Tensor t, int dim, float max_period=10000.0, bool round_bf16=True) -> Tensor")
     D("sampler_update(Tensor x, Tensor net_u, Tensor net_c, Tensor? old_den, Tensor? eps, float c_skip, "
       "float c_out, float cfg, float m1, float m2, float m3, float m4, float mn, int mode) -> (Tensor, Tensor)")
+
+    D("nchw_to_nhwc(Tensor x) -> Tensor")
+    D("groupnorm_stats(Tensor x, int groups=32, float eps=1e-6) -> Tensor")
+    D("im2col3x3(Tensor x, Tensor? gn_stats, Tensor? gamma, Tensor? beta, int groups=32, bool swish=True) -> Tensor")
+    D("pixel_shuffle2(Tensor x) -> Tensor")
+    D("conv3x3_to_nchw16(Tensor x, Tensor w, Tensor? bias) -> Tensor")
+    D("linear_bias_add(Tensor a, Tensor w, Tensor? bias, Tensor add) -> Tensor")
+
+    def _im2col3x3(x, gn_stats, gamma, beta, groups=32, swish=True):
+        gn = None if gn_stats is None else (gn_stats, gamma, beta, groups)
+        return im2col3x3(x, gn=gn, swish=swish)
+
+    def _linear_bias_add(a, w, bias, add):
+        return gemm(a, w, epilogue=EPI_BIAS_ADD, bias=bias, add2=add)
 
     def _attention(q, k, v, variant=0):
         return attention(q, k, v, variant=variant)
@@ -448,7 +578,11 @@ def register_torch_ops() -> None:
                      ("layernorm_modulate", layernorm_modulate), ("final_norm_modulate", final_norm_modulate),
                      ("patchify", _patchify), ("small_linear", small_linear), ("small_linear_batched", _small_linear_batched),
                      ("timestep_embedding", timestep_embedding),
-                     ("sampler_update", _sampler_update)):
+                     ("sampler_update", _sampler_update), ("nchw_to_nhwc", lambda x: nchw_to_nhwc(x)),
+                     ("groupnorm_stats", groupnorm_stats), ("im2col3x3", _im2col3x3),
+                     ("pixel_shuffle2", lambda x: pixel_shuffle2(x)),
+                     ("conv3x3_to_nchw16", lambda x, w, bias: conv3x3_to_nchw16(x, w, bias)),
+                     ("linear_bias_add", _linear_bias_add)):
         lib.impl(name, fn, "CUDA")
     register_torch_ops._lib = lib  # keep alive
     _registered = True
@@ -456,6 +590,7 @@ def register_torch_ops() -> None:
 
 TORCH_OPS = ("attention", "attention_lse", "attention_merge", "linear", "linear_gated_residual", "linear_qkv",
              "linear_bias_pos", "linear_unpatchify", "layernorm_modulate", "final_norm_modulate", "patchify", "small_linear",
-             "small_linear_batched", "timestep_embedding", "sampler_update")
+             "small_linear_batched", "timestep_embedding", "sampler_update", "nchw_to_nhwc", "groupnorm_stats", "im2col3x3",
+             "pixel_shuffle2", "conv3x3_to_nchw16", "linear_bias_add")
 
 register_torch_ops()

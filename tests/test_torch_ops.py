@@ -11,7 +11,7 @@ NS = torch.ops.landiff_b200
 
 
 def test_every_compute_entry_point_is_a_registered_op():
-    assert len(ops.TORCH_OPS) == 15
+    assert len(ops.TORCH_OPS) == 21
     for name in ops.TORCH_OPS:
         op = getattr(NS, name)
         assert "landiff_b200::" + name in str(op.default._schema)
@@ -103,3 +103,18 @@ def test_ops_match_the_ctypes_path():
     # the fp32-row flavour used by the reference-compatible sampler entry
     g3 = NS.sampler_update(xl, nu.float(), nc.float(), old, eps, *kw.values(), 1)
     assert eq(g3[0], g2[0])
+    # conv-stack ops of the semantic conditioner (section 8 row f2)
+    xc = torch.randn(2, 64, 5, 6, device=dev)
+    xl = NS.nchw_to_nhwc(xc)
+    assert eq(xl, ops.nchw_to_nhwc(xc))
+    st = NS.groupnorm_stats(xl, 32, 1e-6)
+    assert eq(st, ops.groupnorm_stats(xl, 32, 1e-6))
+    gmm, btt = (1 + 0.1 * torch.randn(64, device=dev)).bfloat16(), (0.1 * torch.randn(64, device=dev)).bfloat16()
+    assert eq(NS.im2col3x3(xl, st, gmm, btt, 32, True), ops.im2col3x3(xl, gn=(st, gmm, btt, 32)))
+    assert eq(NS.im2col3x3(xl, None, None, None), ops.im2col3x3(xl))
+    assert eq(NS.pixel_shuffle2(xl), ops.pixel_shuffle2(xl))
+    w16 = (torch.randn(16, 64, 3, 3, device=dev) / 24).bfloat16()
+    assert eq(NS.conv3x3_to_nchw16(xl, w16, None), ops.conv3x3_to_nchw16(xl, w16, None))
+    addt = torch.randn(M, D, device=dev).bfloat16()
+    assert eq(NS.linear_bias_add(a, w, bias, addt), ops.gemm(a, w, epilogue=ops.EPI_BIAS_ADD, bias=bias, add2=addt))
+    assert torch.allclose(NS.linear_bias_add(a, w, bias, addt).float(), NS.linear(a, w, bias, 1).float() + addt.float(), atol=0.05)
