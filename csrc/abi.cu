@@ -107,6 +107,56 @@ int make_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t*
   return LD_OK;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeIm2colFn>(p);
+  });
+  return fn;
+}
+
+// im2col-mode tensor map over channels-last bf16 activations [F, H, W, C] for a 3x3 / stride 1 / padding 1 convolution:
+// one load brings `pixels` consecutive output positions (raster order over x, y, frame) x 64 channels of ONE filter tap into
+// a SWIZZLE_128B tile; the tap is given per load as the (kx, ky) offsets, out-of-image taps are zero-filled (the padding).
+// Bounding box: lower corner = -padding = -1, upper corner = padding - (3 - 1) = -1 in x and y.
+int make_tmap_im2col3x3_bf16(CUtensorMap* out, const void* gptr, int C, int W, int H, int F, int pixels) {
+  EncodeIm2colFn enc = get_encode_im2col();
+  if (!enc) {
+    set_error("cuTensorMapEncodeIm2col driver entry point unavailable");
+    return LD_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(gptr) & 15) != 0 || C % 64 != 0) {
+    set_error("im2col TMA source %p must be 16-byte aligned with C=%d a multiple of 64", gptr, C);
+    return LD_ERR_ARG;
+  }
+  const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)F};
+  const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const int lower[2] = {-1, -1}, upper[2] = {-1, -1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(gptr), gdim, gstr, lower, upper, 64u,
+                   (cuuint32_t)pixels, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed with CUresult %d (C %d W %d H %d F %d)", (int)r, C, W, H, F);
+    return LD_ERR_CUDA;
+  }
+  // drivers up to 13.1 set a descriptor bit that breaks im2col loads from tensors smaller than 128 KB (the same fix-up is
+  // applied by CUTLASS, cute/atom/copy_traits_sm90_im2col.hpp)
+  int drv = 0;
+  if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 && (uint64_t)F * H * W * C * 2 < 131072)
+    reinterpret_cast<uint64_t*>(out)[1] &= ~(1llu << 21);
+  return LD_OK;
+}
+
 }  // namespace ld
 
 extern "C" {

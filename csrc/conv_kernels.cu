@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const TX* __restrict_
 // x: [F, P, C] -> stats [F, G, 2] = (mean, rstd), two passes like torch's kernel (sum, then centred squares) and
 // DETERMINISTIC: every CTA reduces its 256-row chunk in a fixed order into partial[f, chunk, g], a one-CTA-per-frame
 // kernel adds the chunks in order.  (vq_gan_blocks.py:35-38: 32 groups, eps 1e-6)
-constexpr int kGnRows = 256;
+constexpr int kGnRows = 64;
 
 template <int PASS>
 __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
@@ -67,16 +67,26 @@ __global__ void __launch_bounds__(256) gn_partial_kernel(const bf16* __restrict_
   const int p0 = blockIdx.x * kGnRows;
   const int p1 = min(P, p0 + kGnRows);
   const uint4* xf = reinterpret_cast<const uint4*>(x + (int64_t)f * P * C);
-  for (int p = p0 + rl; p < p1; p += rstep) {
-    float e[8];
-    cv_unpack8(xf[(int64_t)p * nvec + v], e);
+  for (int pb = p0 + rl; pb < p1; pb += 4 * rstep) {   // four independent 16-byte loads in flight per thread
+    uint4 raw[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (PASS == 1) {
-        const float d = e[i] - mean[i];
-        acc[i] = fmaf(d, d, acc[i]);
-      } else {
-        acc[i] += e[i];
+    for (int u = 0; u < 4; ++u) {
+      const int p = pb + u * rstep;
+      raw[u] = p < p1 ? xf[(int64_t)p * nvec + v] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (pb + u * rstep >= p1) break;
+      float e[8];
+      cv_unpack8(raw[u], e);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (PASS == 1) {
+          const float d = e[i] - mean[i];
+          acc[i] = fmaf(d, d, acc[i]);
+        } else {
+          acc[i] += e[i];
+        }
       }
     }
   }
@@ -100,6 +110,31 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __r
     for (int k = 0; k < nchunk; ++k) s += partial[((int64_t)f * nchunk + k) * G + g];
     if (PASS == 0) stats[(f * G + g) * 2] = s / count;
     else stats[(f * G + g) * 2 + 1] = rsqrtf(s / count + eps);
+  }
+}
+
+// ---- out = swish(GroupNorm(x)): the activation in front of every convolution, applied once --------------------------------
+__global__ void __launch_bounds__(256) gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ out,
+                                                       const float* __restrict__ stats, const bf16* __restrict__ gamma,
+                                                       const bf16* __restrict__ beta, int64_t P, int C, int G, int swish,
+                                                       int64_t total_vec) {
+  const int nvec = C >> 3;
+  const int cpg = C / G;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    const int f = (int)(i / (P * nvec));
+    float e[8], gm[8], bt[8];
+    cv_unpack8(reinterpret_cast<const uint4*>(x)[i], e);
+    cv_unpack8(reinterpret_cast<const uint4*>(gamma)[v], gm);
+    cv_unpack8(reinterpret_cast<const uint4*>(beta)[v], bt);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float2 ms = reinterpret_cast<const float2*>(stats)[f * G + (8 * v + k) / cpg];
+      float y = fmaf((e[k] - ms.x) * ms.y, gm[k], bt[k]);
+      if (swish) y = y / (1.0f + __expf(-y));
+      e[k] = y;
+    }
+    reinterpret_cast<uint4*>(out)[i] = cv_pack8(e);
   }
 }
 
@@ -253,6 +288,20 @@ extern "C" int ld_groupnorm_stats(const void* x, float* stats, float* scratch, i
   gn_finalize_kernel<0><<<frames, 64, 0, st>>>(scratch, stats, nchunk, groups, count, eps);
   gn_partial_kernel<1><<<grid, 256, smem, st>>>((const bf16*)x, stats, scratch, P, C, groups);
   gn_finalize_kernel<1><<<frames, 64, 0, st>>>(scratch, stats, nchunk, groups, count, eps);
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}
+
+extern "C" int ld_groupnorm_apply(const void* x, void* out, const float* stats, const void* gamma, const void* beta, int frames,
+                                  int P, int C, int groups, int swish, void* stream) {
+  using namespace ld;
+  int rc = check_device();
+  if (rc != LD_OK) return rc;
+  LD_CHECK_ARG(x && out && stats && gamma && beta && frames > 0 && P > 0, "ld_groupnorm_apply: bad arguments");
+  LD_CHECK_ARG(C % 8 == 0 && groups > 0 && C % groups == 0, "ld_groupnorm_apply: C=%d must be a multiple of 8 and of groups", C);
+  const int64_t total_vec = (int64_t)frames * P * (C / 8);
+  gn_apply_kernel<<<grid_1d(total_vec, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)out, stats, (const bf16*)gamma,
+                                                                             (const bf16*)beta, P, C, groups, swish, total_vec);
   LD_CHECK_CUDA(cudaGetLastError());
   return LD_OK;
 }

@@ -334,14 +334,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const bool leader = elect_one();
     int s = 0;
     uint32_t ph = 0;
+    const bool conv = p.conv_W > 0;   // implicit 3x3 convolution: A tiles gathered by TMA in im2col mode
+    const int cblocks = conv ? p.conv_C / Cfg::BK : 1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / num_n) * Cfg::BM;
       const int n0 = (tile % num_n) * BN;
+      // first output position of the tile -> base pixel in bounding-box coordinates (lower corner = -padding)
+      const int cx = conv ? m0 % p.conv_W - 1 : 0;
+      const int cy = conv ? (m0 / p.conv_W) % p.conv_H - 1 : 0;
+      const int cf = conv ? m0 / (p.conv_W * p.conv_H) : 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (leader) {
           mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          tma_load_2d(sA + s * Cfg::A_BYTES, &tmap_a, &full_bar[s], kb * Cfg::BK, m0);
+          if (conv) {
+            const int tap = kb / cblocks;
+            tma_load_im2col_4d(sA + s * Cfg::A_BYTES, &tmap_a, &full_bar[s], (kb - tap * cblocks) * Cfg::BK, cx, cy, cf,
+                               (uint16_t)(tap % 3), (uint16_t)(tap / 3));
+          } else {
+            tma_load_2d(sA + s * Cfg::A_BYTES, &tmap_a, &full_bar[s], kb * Cfg::BK, m0);
+          }
           tma_load_2d(sB + s * Cfg::B_BYTES, &tmap_b, &full_bar[s], kb * Cfg::BK, n0);
         }
         if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
@@ -659,7 +671,10 @@ template <int BN, int EPI>
 static int launch_gemm(const ld_gemm_args& a, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap ta, tb;
-  {
+  if (a.conv_W > 0) {
+    int rc = make_tmap_im2col3x3_bf16(&ta, a.A, a.conv_C, a.conv_W, a.conv_H, a.conv_F, 128);
+    if (rc != LD_OK) return rc;
+  } else {
     const uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
     const uint64_t str[1] = {(uint64_t)a.K * 2};
     const uint32_t box[2] = {64, 128};
@@ -701,7 +716,7 @@ template <int EPI>
 static int dispatch_bn(const ld_gemm_args& a, cudaStream_t stream) {
   if constexpr (EPI != LD_EPI_UNPATCHIFY && EPI != LD_EPI_BIAS_POS) {
     // the five per-layer GEMMs (QKV, out-proj, fc1, fc2, zero-linear): CTA pairs, 256 x 192 tiles
-    if (a.N % 192 == 0 && a.M >= 256 && use_pair_kernel()) return launch_gemm2<EPI>(a, stream);
+    if (a.N % 192 == 0 && a.M >= 256 && a.conv_W == 0 && use_pair_kernel()) return launch_gemm2<EPI>(a, stream);
   }
   if (a.N % 192 == 0) return launch_gemm<192, EPI>(a, stream);
   if (a.N % 128 == 0) return launch_gemm<128, EPI>(a, stream);
@@ -722,6 +737,13 @@ extern "C" int ld_gemm_bf16(const ld_gemm_args* args, void* stream) {
   LD_CHECK_ARG(a.A && a.W, "ld_gemm_bf16: null operand");
   LD_CHECK_ARG(a.rows_per_batch > 0 && a.M % a.rows_per_batch == 0,
                "ld_gemm_bf16: M=%d not a multiple of rows_per_batch=%d", a.M, a.rows_per_batch);
+  if (a.conv_W > 0) {
+    LD_CHECK_ARG(a.conv_F > 0 && a.conv_H > 0 && a.conv_C > 0 && a.conv_C % 64 == 0 && a.K == 9 * a.conv_C &&
+                     (int64_t)a.M == (int64_t)a.conv_F * a.conv_H * a.conv_W,
+                 "ld_gemm_bf16: implicit convolution needs conv_C %% 64 == 0, K == 9*conv_C and M == conv_F*conv_H*conv_W");
+    LD_CHECK_ARG(a.epilogue == LD_EPI_NONE || a.epilogue == LD_EPI_BIAS || a.epilogue == LD_EPI_BIAS_GELU ||
+                     a.epilogue == LD_EPI_BIAS_ADD, "ld_gemm_bf16: implicit convolution supports the plain epilogues only");
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a.epilogue != LD_EPI_QKV) {
     LD_CHECK_ARG(a.out != nullptr, "ld_gemm_bf16: null out");

@@ -19,6 +19,8 @@ int sm_count();
 // dims/strides innermost first; strides in BYTES for dims 1.. (dim 0 is contiguous).
 int make_tmap_bf16(CUtensorMap* out, const void* gptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
+// im2col-mode map over channels-last bf16 [F, H, W, C] for a 3x3 / stride 1 / padding 1 convolution (abi.cu)
+int make_tmap_im2col3x3_bf16(CUtensorMap* out, const void* gptr, int C, int W, int H, int F, int pixels);
 
 #define LD_CHECK_ARG(cond, ...)      \
   do {                               \

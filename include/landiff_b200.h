@@ -78,6 +78,10 @@ typedef struct ld_gemm_args {
   /* residual-stream dtype (GATED_RESID: resid/out, BIAS_POS: out): 0 = bf16 (the reference's rounding points),
      1 = fp32 (the main net keeps its 30-layer residual stream in fp32; add2 stays bf16) */
   int32_t resid_f32, out_f32;
+  /* implicit 3x3 convolution (conv_W > 0): A is a channels-last activation tensor [conv_F, conv_H, conv_W, conv_C] bf16
+     (conv_C % 64 == 0), W is [N, 9*conv_C] in (ky, kx, cin) order, K = 9*conv_C, M = conv_F*conv_H*conv_W output positions
+     in raster order; stride 1, zero padding 1.  The A tiles are gathered by TMA in im2col mode (no im2col buffer). */
+  int32_t conv_F, conv_H, conv_W, conv_C;
 } ld_gemm_args;
 
 int ld_gemm_bf16(const ld_gemm_args* args, void* stream);
@@ -190,12 +194,17 @@ int ld_sampler_update(const float* x, const void* net_u, const void* net_c, cons
    channels-last bf16 [frames, H, W, C]; a 3x3 convolution = ld_im2col3x3 (GroupNorm + swish of the input applied on the
    fly) + ld_gemm_bf16 with weights reordered to [Cout, (ky, kx, cin)] and epilogue LD_EPI_BIAS / LD_EPI_BIAS_ADD. */
 
+/* out = swish(GroupNorm(x)) (swish optional) on channels-last frames [frames, P, C] bf16 with ld_groupnorm_stats' (mean, rstd)
+   and gamma/beta bf16 [C]: the activation in front of every convolution (vq_gan_blocks.py:128-140, 599-604) */
+int ld_groupnorm_apply(const void* x, void* out, const float* stats, const void* gamma, const void* beta, int frames, int P,
+                       int C, int groups, int swish, void* stream);
+
 /* x [frames, C, P] (NCHW with P = H*W; bf16 or fp32) -> out [frames, P, C] bf16   (condition.py:104-107 input cast + layout) */
 int ld_nchw_to_nhwc(const void* x, int x_is_f32, void* out, int frames, int C, int P, void* stream);
 
 /* GroupNorm statistics (vq_gan_blocks.py:35-38: 32 groups, eps 1e-6) of channels-last frames x [frames, P, C] bf16:
    stats [frames, groups, 2] fp32 = (mean, rstd), two passes (sum, then centred squares) reduced in a fixed order, so the
-   result is bit-reproducible.  scratch: fp32 [frames * ceil(P / 256) * groups]. */
+   result is bit-reproducible.  scratch: fp32 [frames * ceil(P / 64) * groups]. */
 int ld_groupnorm_stats(const void* x, float* stats, float* scratch, int frames, int P, int C, int groups, float eps,
                        void* stream);
 

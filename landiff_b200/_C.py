@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("pos", C.c_void_p),
         ("T", C.c_int32), ("Hp", C.c_int32), ("Wp", C.c_int32), ("C", C.c_int32),
         ("resid_f32", C.c_int32), ("out_f32", C.c_int32),
+        ("conv_F", C.c_int32), ("conv_H", C.c_int32), ("conv_W", C.c_int32), ("conv_C", C.c_int32),
     ]
 
 
@@ -57,6 +58,7 @@ SIGNATURES = {
     "ld_attention_merge": (C.c_int, [_fp, _fp, _fp, _fp, _vp, _i, _i, _i, _vp]),
     "ld_nchw_to_nhwc": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _vp]),
     "ld_groupnorm_stats": (C.c_int, [_vp, _fp, _fp, _i, _i, _i, _i, C.c_float, _vp]),
+    "ld_groupnorm_apply": (C.c_int, [_vp, _vp, _fp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "ld_im2col3x3": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _fp, _vp, _vp, _i, _i, _vp]),
     "ld_pixel_shuffle2": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ld_conv3x3_to_nchw16": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

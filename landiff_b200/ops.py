@@ -48,15 +48,24 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, epilogue: int, bias: Optional[torc
          add2: Optional[torch.Tensor] = None, gate_img: Optional[torch.Tensor] = None,
          gate_txt: Optional[torch.Tensor] = None, mod_batch_stride: int = 0, qkv=None, qk_ln=None, ln_eps: float = 1e-6,
          q_scale: float = 1.0, heads: int = 0, qkv_row_offset: int = 0, pos: Optional[torch.Tensor] = None,
-         patch_grid=None) -> Optional[torch.Tensor]:
-    """out = epilogue(a @ w.T).  a: [M,K] bf16, w: [N,K] bf16.  See include/landiff_b200.h for the epilogues."""
+         patch_grid=None, conv: bool = False) -> Optional[torch.Tensor]:
+    """out = epilogue(a @ w.T).  a: [M,K] bf16, w: [N,K] bf16.  See include/landiff_b200.h for the epilogues.
+    conv=True: implicit 3x3 / stride 1 / padding 1 convolution — a is a channels-last activation tensor [F, H, W, C] and
+    w is [N, 9*C] in (ky, kx, cin) order; the A tiles are gathered by TMA in im2col mode, M = F*H*W."""
     _chk(a, BF16, "a")
     _chk(w, BF16, "w")
-    M, K = a.shape
+    g = GemmArgs()
+    if conv:
+        if a.dim() != 4 or a.shape[3] % 64:
+            raise ValueError("gemm(conv=True): a must be channels-last [F, H, W, C] with C a multiple of 64")
+        F_, H_, W_, C_ = a.shape
+        M, K = F_ * H_ * W_, 9 * C_
+        g.conv_F, g.conv_H, g.conv_W, g.conv_C = F_, H_, W_, C_
+    else:
+        M, K = a.shape
     N, K2 = w.shape
     if K != K2:
         raise ValueError(f"gemm: inner dims differ ({K} vs {K2})")
-    g = GemmArgs()
     g.M, g.N, g.K, g.epilogue = M, N, K, epilogue
     g.A, g.W = a.data_ptr(), w.data_ptr()
     if bias is not None:
@@ -381,10 +390,25 @@ def groupnorm_stats(x: torch.Tensor, groups: int = 32, eps: float = 1e-6) -> tor
     _chk(x, BF16, "x")
     F_, H, W, C_ = x.shape
     stats = torch.empty((F_, groups, 2), dtype=F32, device=x.device)
-    scratch = torch.empty((F_ * ((H * W + 255) // 256) * groups,), dtype=F32, device=x.device)
+    scratch = torch.empty((F_ * ((H * W + 63) // 64) * groups,), dtype=F32, device=x.device)
     check(_C.load().ld_groupnorm_stats(x.data_ptr(), stats.data_ptr(), scratch.data_ptr(), F_, H * W, C_, groups, float(eps),
                                        _stream()), "ld_groupnorm_stats")
     return stats
+
+
+def groupnorm_apply(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int = 32,
+                    swish: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """swish(GroupNorm(x)) on channels-last frames [F, H, W, C] bf16 with `groupnorm_stats`' (mean, rstd)."""
+    _chk(x, BF16, "x"); _chk(stats, F32, "stats"); _chk(gamma, BF16, "gamma"); _chk(beta, BF16, "beta")
+    F_, H, W, C_ = x.shape
+    if stats.numel() != F_ * groups * 2 or gamma.numel() != C_ or beta.numel() != C_:
+        raise ValueError("groupnorm_apply: operand sizes")
+    if out is None:
+        out = torch.empty_like(x)
+    _chk(out, BF16, "out")
+    check(_C.load().ld_groupnorm_apply(x.data_ptr(), out.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), F_,
+                                       H * W, C_, int(groups), 1 if swish else 0, _stream()), "ld_groupnorm_apply")
+    return out
 
 
 def im2col3x3(x: torch.Tensor, out: Optional[torch.Tensor] = None, *, gn=None, swish: bool = True) -> torch.Tensor:
@@ -441,14 +465,24 @@ def conv3x3_to_nchw16(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Ten
 
 
 def conv3x3(x: torch.Tensor, w_taps: torch.Tensor, bias: Optional[torch.Tensor], *, gn=None, swish: bool = True,
-            add: Optional[torch.Tensor] = None, col: Optional[torch.Tensor] = None, max_col_bytes: int = 256 << 20):
-    """3x3 / stride 1 / padding 1 convolution on channels-last frames as im2col + tcgen05 GEMM.  w_taps: [Cout, 9*Cin] bf16
-    in (ky, kx, cin) order (`conv_weight_taps`); gn / swish: see im2col3x3; add: residual [F, H, W, Cout] added in the GEMM
-    epilogue.  Frames are processed in chunks so that the im2col buffer stays under max_col_bytes."""
+            add: Optional[torch.Tensor] = None, implicit: bool = True, col: Optional[torch.Tensor] = None,
+            max_col_bytes: int = 256 << 20):
+    """3x3 / stride 1 / padding 1 convolution on channels-last frames on the tcgen05 GEMM.  w_taps: [Cout, 9*Cin] bf16 in
+    (ky, kx, cin) order (`conv_weight_taps`); gn = (stats, gamma, beta, groups): GroupNorm (+ swish) of the input first;
+    add: residual [F, H, W, Cout] added in the GEMM epilogue.
+    implicit=True (Cin % 64 == 0): the activation is applied once and the GEMM gathers its A tiles by TMA in im2col mode —
+    no im2col buffer.  implicit=False: explicit im2col (activation fused into the gather) + plain GEMM, in frame chunks
+    so that the buffer stays under max_col_bytes."""
     _chk(x, BF16, "x")
     F_, H, W, Cin = x.shape
     Cout = w_taps.shape[0]
     out = torch.empty((F_, H, W, Cout), dtype=BF16, device=x.device)
+    epi = EPI_BIAS if add is None else EPI_BIAS_ADD
+    if implicit and Cin % 64 == 0:
+        a = x if gn is None else groupnorm_apply(x, gn[0], gn[1], gn[2], gn[3], swish)
+        gemm(a, w_taps, epilogue=epi, bias=bias, out=out.view(-1, Cout), conv=True,
+             add2=None if add is None else add.view(-1, Cout))
+        return out
     per_frame = H * W * 9 * Cin * 2
     chunk = max(1, min(F_, max_col_bytes // per_frame))
     if col is None or col.numel() < chunk * H * W * 9 * Cin:
@@ -457,11 +491,8 @@ def conv3x3(x: torch.Tensor, w_taps: torch.Tensor, bias: Optional[torch.Tensor],
         f1 = min(F_, f0 + chunk)
         g = None if gn is None else (gn[0][f0:f1], gn[1], gn[2], gn[3])
         a = im2col3x3(x[f0:f1], col[: (f1 - f0) * H * W * 9 * Cin].view((f1 - f0) * H * W, 9 * Cin), gn=g, swish=swish)
-        o = out[f0:f1].view(-1, Cout)
-        if add is None:
-            gemm(a, w_taps, epilogue=EPI_BIAS, bias=bias, out=o)
-        else:
-            gemm(a, w_taps, epilogue=EPI_BIAS_ADD, bias=bias, out=o, add2=add[f0:f1].view(-1, Cout))
+        gemm(a, w_taps, epilogue=epi, bias=bias, out=out[f0:f1].view(-1, Cout),
+             add2=None if add is None else add[f0:f1].view(-1, Cout))
     return out
 
 
@@ -508,6 +539,8 @@ def register_torch_ops() -> None:
 
     D("nchw_to_nhwc(Tensor x) -> Tensor")
     D("groupnorm_stats(Tensor x, int groups=32, float eps=1e-6) -> Tensor")
+    D("groupnorm_apply(Tensor x, Tensor stats, Tensor gamma, Tensor beta, int groups=32, bool swish=True) -> Tensor")
+    D("conv3x3(Tensor x, Tensor w_taps, Tensor? bias, Tensor? add) -> Tensor")
     D("im2col3x3(Tensor x, Tensor? gn_stats, Tensor? gamma, Tensor? beta, int groups=32, bool swish=True) -> Tensor")
     D("pixel_shuffle2(Tensor x) -> Tensor")
     D("conv3x3_to_nchw16(Tensor x, Tensor w, Tensor? bias) -> Tensor")
@@ -580,6 +613,8 @@ def register_torch_ops() -> None:
                      ("timestep_embedding", timestep_embedding),
                      ("sampler_update", _sampler_update), ("nchw_to_nhwc", lambda x: nchw_to_nhwc(x)),
                      ("groupnorm_stats", groupnorm_stats), ("im2col3x3", _im2col3x3),
+                     ("groupnorm_apply", lambda x, st, gm, bt, groups=32, swish=True: groupnorm_apply(x, st, gm, bt, groups, swish)),
+                     ("conv3x3", lambda x, w_taps, bias, add: conv3x3(x, w_taps, bias, add=add)),
                      ("pixel_shuffle2", lambda x: pixel_shuffle2(x)),
                      ("conv3x3_to_nchw16", lambda x, w, bias: conv3x3_to_nchw16(x, w, bias)),
                      ("linear_bias_add", _linear_bias_add)):
@@ -590,7 +625,7 @@ def register_torch_ops() -> None:
 
 TORCH_OPS = ("attention", "attention_lse", "attention_merge", "linear", "linear_gated_residual", "linear_qkv",
              "linear_bias_pos", "linear_unpatchify", "layernorm_modulate", "final_norm_modulate", "patchify", "small_linear",
-             "small_linear_batched", "timestep_embedding", "sampler_update", "nchw_to_nhwc", "groupnorm_stats", "im2col3x3",
+             "small_linear_batched", "timestep_embedding", "sampler_update", "nchw_to_nhwc", "groupnorm_stats", "groupnorm_apply", "conv3x3", "im2col3x3",
              "pixel_shuffle2", "conv3x3_to_nchw16", "linear_bias_add")
 
 register_torch_ops()

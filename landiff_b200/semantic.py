@@ -145,7 +145,7 @@ class Decoder(nn.Module):
         self.conv_out = _Conv(block_in, out_ch)
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:
-        col = torch.empty((256 << 20) // 2, dtype=BF16, device=z.device)   # one im2col buffer for the whole pass
+        col = None   # every width here is a multiple of 64: implicit convolution, no im2col buffer
         h = ops.conv3x3(z, self.conv_in.taps(), self.conv_in.bias, col=col)
         h = self.mid.block_1(h, col)
         h = self.mid.block_2(h, col)

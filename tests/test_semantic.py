@@ -120,14 +120,27 @@ def test_cuda_kernels_against_torch():
     bt = (0.1 * torch.randn(C_, device=dev)).bfloat16()
     xn = xl.float().permute(0, 3, 1, 2)
     ref_plain = torch.nn.functional.conv2d(xn, w.float(), b.float(), padding=1)
-    got = ops.conv3x3(xl, ops.conv_weight_taps(w), b)
+    got = ops.conv3x3(xl, ops.conv_weight_taps(w), b)                       # implicit: TMA im2col-mode gather
     assert rel(got.float().permute(0, 3, 1, 2), ref_plain) < 4e-3
+    got_x = ops.conv3x3(xl, ops.conv_weight_taps(w), b, implicit=False)     # explicit im2col buffer
+    assert torch.equal(got, got_x)                                          # same MMA order, same operands: bit-equal
     act = torch.nn.functional.group_norm(xn, 32, gm.float(), bt.float(), eps=1e-6)
     act = act * torch.sigmoid(act)
     add = torch.randn(F_, H, W, 64, device=dev).bfloat16()
     ref_gn = torch.nn.functional.conv2d(act, w.float(), b.float(), padding=1) + add.float().permute(0, 3, 1, 2)
-    got = ops.conv3x3(xl, ops.conv_weight_taps(w), b, gn=(st, gm, bt, 32), add=add, max_col_bytes=H * W * 9 * C_ * 2)
+    got = ops.conv3x3(xl, ops.conv_weight_taps(w), b, gn=(st, gm, bt, 32), add=add)
     assert rel(got.float().permute(0, 3, 1, 2), ref_gn) < 6e-3     # bf16 rounding of the activated input + output
+    got_x = ops.conv3x3(xl, ops.conv_weight_taps(w), b, gn=(st, gm, bt, 32), add=add, implicit=False,
+                        max_col_bytes=H * W * 9 * C_ * 2)           # one frame per chunk
+    assert torch.equal(got, got_x)
+    assert rel(ops.groupnorm_apply(xl, st, gm, bt, 32, True).float(), act.permute(0, 2, 3, 1)) < 4e-3
+    # a multi-tile, multi-frame implicit convolution whose 128-position tiles straddle rows and frames
+    xb = torch.randn(5, 13, 17, 192, device=dev).bfloat16()
+    wb = (torch.randn(128, 192, 3, 3, device=dev) / (9 * 192) ** 0.5).bfloat16()
+    ref_b = torch.nn.functional.conv2d(xb.float().permute(0, 3, 1, 2), wb.float(), None, padding=1)
+    got_b = ops.conv3x3(xb, ops.conv_weight_taps(wb), None)
+    assert rel(got_b.float().permute(0, 3, 1, 2), ref_b) < 4e-3
+    assert torch.equal(got_b, ops.conv3x3(xb, ops.conv_weight_taps(wb), None, implicit=False))
     # pixel shuffle
     ps = ops.pixel_shuffle2(xl)
     assert torch.equal(ps.permute(0, 3, 1, 2), torch.nn.functional.pixel_shuffle(xl.permute(0, 3, 1, 2), 2))

@@ -11,7 +11,7 @@ NS = torch.ops.landiff_b200
 
 
 def test_every_compute_entry_point_is_a_registered_op():
-    assert len(ops.TORCH_OPS) == 21
+    assert len(ops.TORCH_OPS) == 23
     for name in ops.TORCH_OPS:
         op = getattr(NS, name)
         assert "landiff_b200::" + name in str(op.default._schema)
@@ -112,6 +112,9 @@ def test_ops_match_the_ctypes_path():
     gmm, btt = (1 + 0.1 * torch.randn(64, device=dev)).bfloat16(), (0.1 * torch.randn(64, device=dev)).bfloat16()
     assert eq(NS.im2col3x3(xl, st, gmm, btt, 32, True), ops.im2col3x3(xl, gn=(st, gmm, btt, 32)))
     assert eq(NS.im2col3x3(xl, None, None, None), ops.im2col3x3(xl))
+    assert eq(NS.groupnorm_apply(xl, st, gmm, btt, 32, True), ops.groupnorm_apply(xl, st, gmm, btt, 32, True))
+    wt = ops.conv_weight_taps((torch.randn(64, 64, 3, 3, device=dev) / 24).bfloat16())
+    assert eq(NS.conv3x3(xl, wt, None, None), ops.conv3x3(xl, wt, None))
     assert eq(NS.pixel_shuffle2(xl), ops.pixel_shuffle2(xl))
     w16 = (torch.randn(16, 64, 3, 3, device=dev) / 24).bfloat16()
     assert eq(NS.conv3x3_to_nchw16(xl, w16, None), ops.conv3x3_to_nchw16(xl, w16, None))
