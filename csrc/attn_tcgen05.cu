@@ -40,6 +40,7 @@ struct alignas(64) AttnShards {
   int nkv[kMaxShards];
   int n;                                 // shards
   int n_sub;                             // 64-key sub-blocks over all shards
+  int n_box;                             // 128-key TMA boxes over all shards
   uint32_t* status;                      // [0] |= 1 when a shard wait gave up after wait_cycles (result invalid)
   long long wait_cycles;
 };
@@ -54,7 +55,53 @@ struct AttnParams {
   int q_rows;
   int exact_only;    // variant 1: run the exact path for every CTA
   long long* prof;   // per-(CTA, warp) phase cycle counters (profiling build of the fast path only)
+  // Tail split (wave quantisation): CTAs [0, n_main) each own one (head, 256-row query block) over ALL keys; the remaining
+  // query blocks — the last, partial wave of the grid — are each served by n_split CTAs that take 1/n_split of the key
+  // boxes and write normalised fp32 partial outputs + log-sum-exp, merged by attn_split_merge_kernel.  n_split <= 1: off.
+  int n_main, n_split;
+  float* part_o;     // [tail block][split][256][64]
+  float* part_lse;   // [tail block][split][256]
 };
+
+// What one CTA works on: logical (head, query block) index, its range of key boxes, where its result goes.
+struct AttnWork {
+  int cta;           // logical work index: bh * q_blocks + query block
+  int gb0, gb1;      // global box range [gb0, gb1) over the concatenated shards
+  int n_sub;         // 64-key sub-blocks inside the range
+  int64_t part_row;  // >= 0: first row of this CTA's slot in part_o / part_lse; < 0: final output
+};
+
+__device__ __forceinline__ int range_sub_blocks(const AttnShards& sh, int gb0, int gb1) {
+  int n = 0, box0 = 0;
+  for (int s = 0; s < sh.n; ++s) {
+    const int nb = (sh.nkv[s] + 127) >> 7, ns = (sh.nkv[s] + 63) >> 6;
+    const int lo = max(gb0, box0), hi = min(gb1, box0 + nb);
+    if (hi > lo) n += min(ns, 2 * (hi - box0)) - 2 * (lo - box0);
+    box0 += nb;
+  }
+  return n;
+}
+
+__device__ __forceinline__ AttnWork attn_work(const AttnShards& sh, const AttnParams& p) {
+  AttnWork w;
+  const int x = blockIdx.x;
+  if (p.n_split <= 1 || x < p.n_main) {
+    w.cta = x;
+    w.gb0 = 0;
+    w.gb1 = sh.n_box;
+    w.n_sub = sh.n_sub;
+    w.part_row = -1;
+  } else {
+    const int idx = x - p.n_main;
+    const int tb = idx / p.n_split, j = idx - tb * p.n_split;
+    w.cta = p.n_main + tb;
+    w.gb0 = (int)((int64_t)sh.n_box * j / p.n_split);
+    w.gb1 = (int)((int64_t)sh.n_box * (j + 1) / p.n_split);
+    w.n_sub = range_sub_blocks(sh, w.gb0, w.gb1);
+    w.part_row = (int64_t)idx * 256;
+  }
+  return w;
+}
 
 // dynamic shared memory (1024-byte aligned base)
 constexpr int kOffK = 0;
@@ -71,18 +118,23 @@ constexpr int kAttnSmem = kOffSlot + 16 + 1024 /* alignment slack */;
 // Sub-block table entry: box index (20 bits) | half of the box << 20 | last sub-block of its box << 21 | valid keys << 24.
 // Shards are walked box by box (128 keys per TMA box, two 64-key sub-blocks); a shard whose key count is not a multiple
 // of 128 ends with a one-sub-block box, so the (box, half) of sub-block i is not a function of i alone.
-__device__ __forceinline__ void build_sub_table(const AttnShards& sh, uint32_t* tab, int lane) {
-  int i0 = 0, box0 = 0;
+__device__ __forceinline__ void build_sub_table(const AttnShards& sh, uint32_t* tab, int lane, int gb0, int gb1) {
+  int i0 = 0, box0 = 0;   // i0: entries written so far (sub-blocks inside [gb0, gb1)); box indices are relative to gb0
   for (int s = 0; s < sh.n; ++s) {
     const int nkv = sh.nkv[s];
-    const int ns = (nkv + 63) >> 6;
-    for (int l = lane; l < ns; l += 32) {
-      const int valid = min(64, nkv - 64 * l);
-      const uint32_t last = ((l & 1) || l == ns - 1) ? 1u : 0u;
-      tab[i0 + l] = uint32_t(box0 + (l >> 1)) | (uint32_t(l & 1) << 20) | (last << 21) | (uint32_t(valid) << 24);
+    const int ns = (nkv + 63) >> 6, nb = (nkv + 127) >> 7;
+    const int lo = max(gb0, box0), hi = min(gb1, box0 + nb);
+    if (hi > lo) {
+      const int l0 = 2 * (lo - box0), l1 = min(ns, 2 * (hi - box0));
+      for (int l = l0 + lane; l < l1; l += 32) {
+        const int valid = min(64, nkv - 64 * l);
+        const uint32_t last = ((l & 1) || l == ns - 1) ? 1u : 0u;
+        tab[i0 + l - l0] =
+            uint32_t(box0 + (l >> 1) - gb0) | (uint32_t(l & 1) << 20) | (last << 21) | (uint32_t(valid) << 24);
+      }
+      i0 += l1 - l0;
     }
-    i0 += ns;
-    box0 += (nkv + 127) >> 7;
+    box0 += nb;
   }
 }
 __device__ __forceinline__ int tab_box(uint32_t e) { return int(e & 0xFFFFFu); }
@@ -92,10 +144,17 @@ __device__ __forceinline__ int tab_valid(uint32_t e) { return int(e >> 24); }
 
 // TMA producer (one warp, warp-uniform, elect.sync leader): K and V boxes of every shard through kKS-deep mbarrier rings.
 __device__ __forceinline__ void produce_kv(const AttnShards& sh, uint8_t* sK, uint8_t* sV, uint64_t* k_full,
-                                           uint64_t* k_empty, uint64_t* v_full, uint64_t* v_empty, int bh) {
+                                           uint64_t* k_empty, uint64_t* v_full, uint64_t* v_empty, int bh, int gb0,
+                                           int gb1) {
   const bool leader = elect_one();
-  int g = 0;   // global box counter
+  int g = 0;      // box counter of this CTA (ring stage and phase)
+  int box0 = 0;   // global index of the shard's first box
   for (int s = 0; s < sh.n; ++s) {
+    const int nb_s = (sh.nkv[s] + 127) >> 7;
+    const int lo = max(gb0, box0), hi = min(gb1, box0 + nb_s);
+    const int j0 = lo - box0, j1 = hi - box0;
+    box0 += nb_s;
+    if (j1 <= j0) continue;   // no box of this shard in the CTA's key range: its arrival is not waited for either
     if (sh.ready[s] != nullptr) {
       // the shard is being written by a peer's copy engine: wait for its arrival flag (written after the copy)
       if (leader) {
@@ -111,8 +170,7 @@ __device__ __forceinline__ void produce_kv(const AttnShards& sh, uint8_t* sK, ui
       }
       __syncwarp();
     }
-    const int nb = (sh.nkv[s] + 127) >> 7;
-    for (int j = 0; j < nb; ++j, ++g) {
+    for (int j = j0; j < j1; ++j, ++g) {
       const int st = g % kKS;
       const uint32_t ph = (g / kKS) & 1;
       mbar_wait(&k_empty[st], ph ^ 1);
@@ -182,7 +240,7 @@ __device__ __forceinline__ void ex2_poly_pair(uint64_t x2, float& p0, float& p1)
 //   TMEM columns: S/P(stream) at 64*stream [0,256) ; O(stream) at 256 + 64*stream [256,512)
 // All 640 threads must call this (it initialises its own barrier set and synchronises the CTA).
 __device__ __forceinline__ void attn_exact_body(const AttnShards& sh, const AttnParams& p, uint8_t* smem,
-                                                uint32_t tmem_base, int cta, int cw, int sw0) {
+                                                uint32_t tmem_base, const AttnWork& wk, int cw, int sw0) {
   uint8_t* sK = smem + kOffK;
   uint8_t* sV = smem + kOffV;
   uint8_t* sQ = smem + kOffQ;
@@ -201,9 +259,9 @@ __device__ __forceinline__ void attn_exact_body(const AttnShards& sh, const Attn
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q_blocks = (p.nq + 255) / 256;
-  const int bh = cta / q_blocks;
-  const int q0 = (cta % q_blocks) * 256;
-  const int n_sub = sh.n_sub;
+  const int bh = wk.cta / q_blocks;
+  const int q0 = (wk.cta % q_blocks) * 256;
+  const int n_sub = wk.n_sub;
 
   if (warp == cw && lane == 0) {
     mbar_init(q_full, 1);
@@ -232,7 +290,7 @@ __device__ __forceinline__ void attn_exact_body(const AttnShards& sh, const Attn
       tma_load_3d(sQ + kTileBytes, &sh.q, q_full, 0, q0 + 128, bh);
     }
     __syncwarp();
-    produce_kv(sh, sK, sV, k_full, k_empty, v_full, v_empty, bh);
+    produce_kv(sh, sK, sV, k_full, k_empty, v_full, v_empty, bh, wk.gb0, wk.gb1);
   } else if (warp == cw + 1) {
     // ------------------------------------------------------------------ MMA issuer
     const bool leader = elect_one();
@@ -415,7 +473,10 @@ __device__ __forceinline__ void attn_exact_body(const AttnShards& sh, const Attn
     }
     tmem_ld_wait();
     if (valid_row) {
+      const bool partial = wk.part_row >= 0;
+      const int64_t prow = wk.part_row + t * 128 + row_in_tile;
       bf16* orow = p.out + ((int64_t)bb * p.nq + q_row) * (p.heads * 64) + h * 64 + c0;
+      float* of_base = partial ? p.part_o + prow * 64 : (p.out_f32 ? p.out_f32 + ((int64_t)bh * p.nq + q_row) * 64 : nullptr);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float f[8];
@@ -426,17 +487,22 @@ __device__ __forceinline__ void attn_exact_body(const AttnShards& sh, const Attn
           if (other_has) v = fmaf(__uint_as_float(ob[g * 8 + e]), f_oth, v);
           f[e] = v;
         }
-        uint4 v;
-        v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
-        v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(orow + g * 8) = v;
-        if (p.out_f32 != nullptr) {
-          float* of = p.out_f32 + ((int64_t)bh * p.nq + q_row) * 64 + c0 + g * 8;
+        if (!partial) {
+          uint4 v;
+          v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+          v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(orow + g * 8) = v;
+        }
+        if (of_base != nullptr) {
+          float* of = of_base + c0 + g * 8;
           *reinterpret_cast<float4*>(of) = make_float4(f[0], f[1], f[2], f[3]);
           *reinterpret_cast<float4*>(of + 4) = make_float4(f[4], f[5], f[6], f[7]);
         }
       }
-      if (b == 0 && p.lse != nullptr) p.lse[(int64_t)bh * p.nq + q_row] = m_all + log2f(l_all);
+      if (b == 0) {
+        if (partial) p.part_lse[prow] = m_all + log2f(l_all);
+        else if (p.lse != nullptr) p.lse[(int64_t)bh * p.nq + q_row] = m_all + log2f(l_all);
+      }
     }
   }
 }
@@ -501,9 +567,10 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q_blocks = (p.nq + 255) / 256;
-  const int bh = blockIdx.x / q_blocks;
-  const int q0 = (blockIdx.x % q_blocks) * 256;
-  const int n_sub = sh.n_sub;
+  const AttnWork wk = attn_work(sh, p);
+  const int bh = wk.cta / q_blocks;
+  const int q0 = (wk.cta % q_blocks) * 256;
+  const int n_sub = wk.n_sub;
 
   if (warp == 17 && lane == 0) {
     tma_prefetch_desc(&sh.q);
@@ -526,7 +593,7 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
     fence_barrier_init();
   }
   if (warp == 16) {
-    build_sub_table(sh, tab, lane);
+    build_sub_table(sh, tab, lane, wk.gb0, wk.gb1);
     for (int i = lane; i < 512; i += 32) sOnes[i] = 0x3F803F80u;   // bf16 1.0 pairs
     fence_proxy_async_smem();   // the ones tile is read by the async proxy (tcgen05.mma B operand)
   }
@@ -542,7 +609,7 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
   if (warp >= 16) reg_dealloc<56>();   // releases 4 x 32 x 40 = 5120 registers
   if (!p.exact_only) {
     if (warp == 17) {
-      produce_kv(sh, sK, sV, k_full, k_empty, v_full, v_empty, bh);
+      produce_kv(sh, sK, sV, k_full, k_empty, v_full, v_empty, bh, wk.gb0, wk.gb1);
     } else if (warp >= 18) {
       // ------------------------------------------------------------------ MMA issuer of query tile t
       const int t = warp - 18;
@@ -765,7 +832,11 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
       const int bb = bh / p.heads, hd = bh - bb * p.heads;
       if (valid_row) {
         bad = !(l_all < INFINITY) || !(l_all > 0.f);   // inf / NaN row sum (or everything flushed to zero)
+        const bool partial = wk.part_row >= 0;
+        const int64_t prow = wk.part_row + t * 128 + row_in_tile;
         bf16* orow = p.out + ((int64_t)bb * p.nq + q_row) * (p.heads * 64) + hd * 64 + c0;
+        float* of_base =
+            partial ? p.part_o + prow * 64 : (p.out_f32 ? p.out_f32 + ((int64_t)bh * p.nq + q_row) * 64 : nullptr);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float f[8];
@@ -774,20 +845,25 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
             f[e] = __uint_as_float(o[g * 8 + e]) * inv_l;
             bad |= !(fabsf(f[e]) < INFINITY);
           }
-          uint4 v;
-          v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
-          v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
-          *reinterpret_cast<uint4*>(orow + g * 8) = v;
-          if (p.out_f32 != nullptr) {
-            float* of = p.out_f32 + ((int64_t)bh * p.nq + q_row) * 64 + c0 + g * 8;
+          if (!partial) {
+            uint4 v;
+            v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+            v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(orow + g * 8) = v;
+          }
+          if (of_base != nullptr) {
+            float* of = of_base + c0 + g * 8;
             *reinterpret_cast<float4*>(of) = make_float4(f[0], f[1], f[2], f[3]);
             *reinterpret_cast<float4*>(of + 4) = make_float4(f[4], f[5], f[6], f[7]);
           }
         }
         // truncated P values are low by 2^-9 on average (uniform mantissa tails): the normalisation above uses the same
         // values and needs no correction, the exported log-sum-exp does
-        if (b == 0 && p.lse != nullptr)
-          p.lse[(int64_t)bh * p.nq + q_row] = msc + log2f(TRUNC ? l_all * 1.001953125f : l_all);
+        if (b == 0) {
+          const float lse_v = msc + log2f(TRUNC ? l_all * 1.001953125f : l_all);
+          if (partial) p.part_lse[prow] = lse_v;
+          else if (p.lse != nullptr) p.lse[(int64_t)bh * p.nq + q_row] = lse_v;
+        }
       }
     }
   } else {
@@ -799,7 +875,7 @@ attn5_kernel(const __grid_constant__ AttnShards sh, const AttnParams p) {
   if (redo) {
     // the fixed reference maximum overflowed somewhere in this CTA's 256 rows (or variant 1): exact path, same launch
     tc_fence_after();
-    attn_exact_body(sh, p, smem, tmem_base, blockIdx.x, /*cw=*/16, /*sw0=*/0);
+    attn_exact_body(sh, p, smem, tmem_base, wk, /*cw=*/16, /*sw0=*/0);
     tc_fence_before();
     __syncthreads();
   }
@@ -839,6 +915,41 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(float* __restrict__ o_a
   if ((gid & 15) == 0) lse_acc[row] = m + log2f(wa + wb);
 }
 
+// Tail split: out rows of tail block tb = sum over its n_split partial results weighted by 2^(lse_j - max lse)
+__global__ void __launch_bounds__(256) attn_split_merge_kernel(const float* __restrict__ part_o,
+                                                               const float* __restrict__ part_lse, bf16* __restrict__ out,
+                                                               int n_main, int n_split, int n_tail, int heads, int nq) {
+  // 16 threads per row (4 floats each), 256 rows per tail block
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = gid >> 4;
+  const int c = (int)(gid & 15) * 4;
+  if (row >= (int64_t)n_tail * 256) return;
+  const int tb = (int)(row >> 8), r = (int)(row & 255);
+  const int q_blocks = (nq + 255) / 256;
+  const int work = n_main + tb;
+  const int bh = work / q_blocks;
+  const int q_row = (work % q_blocks) * 256 + r;
+  if (q_row >= nq) return;
+  const int64_t base = ((int64_t)tb * n_split) * 256 + r;   // partial slot j: base + j * 256
+  float m = -INFINITY;
+  for (int j = 0; j < n_split; ++j) m = fmaxf(m, part_lse[base + (int64_t)j * 256]);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float wsum = 0.f;
+  for (int j = 0; j < n_split; ++j) {
+    const float w = exp2f(part_lse[base + (int64_t)j * 256] - m);
+    const float4 o = *reinterpret_cast<const float4*>(part_o + (base + (int64_t)j * 256) * 64 + c);
+    acc.x = fmaf(o.x, w, acc.x); acc.y = fmaf(o.y, w, acc.y); acc.z = fmaf(o.z, w, acc.z); acc.w = fmaf(o.w, w, acc.w);
+    wsum += w;
+  }
+  const float inv = 1.0f / wsum;
+  const int bb = bh / heads, hd = bh - bb * heads;
+  bf16* o = out + ((int64_t)bb * nq + q_row) * (heads * 64) + hd * 64 + c;
+  uint2 v;
+  v.x = pack_bf16x2(acc.x * inv, acc.y * inv);
+  v.y = pack_bf16x2(acc.z * inv, acc.w * inv);
+  *reinterpret_cast<uint2*>(o) = v;
+}
+
 template <int KP, bool TRUNC, bool PROF = false>
 static int launch_attn5(const AttnShards& sh, const AttnParams& prm, int grid, cudaStream_t st) {
   auto kern = attn5_kernel<KP, TRUNC, PROF>;
@@ -853,6 +964,13 @@ static int launch_attn5(const AttnShards& sh, const AttnParams& prm, int grid, c
   }
   kern<<<grid, kAttnThreads, kAttnSmem, st>>>(sh, prm);
   LD_CHECK_CUDA(cudaGetLastError());
+  if (prm.n_split > 1) {
+    const int n_tail = (grid - prm.n_main) / prm.n_split;
+    const int64_t threads = (int64_t)n_tail * 256 * 16;
+    attn_split_merge_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(prm.part_o, prm.part_lse, prm.out, prm.n_main,
+                                                                               prm.n_split, n_tail, prm.heads, prm.nq);
+    LD_CHECK_CUDA(cudaGetLastError());
+  }
   return LD_OK;
 }
 
@@ -878,6 +996,28 @@ static int status_word(uint32_t** out) {
   return LD_OK;
 }
 
+constexpr int kMaxSplitCtas = 320;   // bound on the CTAs of the split tail (workspace <= 21 MB)
+
+// Tail split plan.  A grid of `grid` equal CTAs on `sms` SMs runs ceil(grid / sms) waves; the last one is partly empty.  Its
+// n_tail query blocks are each split over S key ranges so that the tail costs ceil(n_tail * S / sms) / S (+ a fixed cost per
+// CTA: prologue, first-block reference, epilogue) instead of one full wave.  Returns S (1 = no split).
+static int plan_tail_split(int grid, int sms, int n_box, int* n_main) {
+  static const int enabled = [] { const char* e = getenv("LD_ATTN_SPLIT"); return (e && e[0] == '0') ? 0 : 1; }();
+  *n_main = grid;
+  const int n_tail = grid % sms;
+  if (!enabled || n_tail == 0) return 1;
+  int best = 1;
+  double best_cost = 0.97;   // a split must save at least 3 % of a wave to be worth the merge
+  for (int S = 2; S <= 16; ++S) {
+    if ((int64_t)n_tail * S > kMaxSplitCtas || n_box < 6 * S) break;
+    const double per_cta = 1.0 / S + 0.025 + 1.0 / n_box;   // share of the keys + fixed cost (in units of a full CTA)
+    const double cost = (double)((n_tail * S + sms - 1) / sms) * per_cta;
+    if (cost < best_cost) { best_cost = cost; best = S; }
+  }
+  if (best > 1) *n_main = grid - n_tail;
+  return best;
+}
+
 extern "C" int ld_attention_status(unsigned int* host_out, int reset) {
   uint32_t* w = nullptr;
   int rc = status_word(&w);
@@ -888,9 +1028,31 @@ extern "C" int ld_attention_status(unsigned int* host_out, int reset) {
   return LD_OK;
 }
 
+static int total_boxes(const ld_kv_shard* shards, int n_shards) {
+  int nb = 0;
+  for (int s = 0; s < n_shards; ++s) nb += (shards[s].nkv + 127) / 128;
+  return nb;
+}
+
+extern "C" size_t ld_attention_workspace_bytes(const ld_kv_shard* shards, int n_shards, int batch, int heads, int nq) {
+  if (shards == nullptr || n_shards < 1 || n_shards > kMaxShards || batch <= 0 || heads <= 0 || nq <= 0) return 0;
+  if (check_device() != LD_OK) return 0;
+  const int grid = batch * heads * ((nq + 255) / 256);
+  int n_main = grid;
+  const int S = plan_tail_split(grid, sm_count(), total_boxes(shards, n_shards), &n_main);
+  return S > 1 ? (size_t)(grid - n_main) * S * 256 * 65 * sizeof(float) : 0;
+}
+
 extern "C" int ld_attention_shards_bf16(const void* q, const ld_kv_shard* shards, int n_shards, void* out, float* lse,
                                         float* out_f32, int batch, int heads, int nq, int q_rows, int variant,
                                         void* stream) {
+  return ld_attention_shards_ws_bf16(q, shards, n_shards, out, lse, out_f32, batch, heads, nq, q_rows, variant, nullptr, 0,
+                                     stream);
+}
+
+extern "C" int ld_attention_shards_ws_bf16(const void* q, const ld_kv_shard* shards, int n_shards, void* out, float* lse,
+                                           float* out_f32, int batch, int heads, int nq, int q_rows, int variant,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_device();
   if (rc != LD_OK) return rc;
   LD_CHECK_ARG(q && shards && out, "ld_attention: null pointer");
@@ -923,6 +1085,7 @@ extern "C" int ld_attention_shards_bf16(const void* q, const ld_kv_shard* shards
     sh.ready[s] = d.ready_flag;
     sh.ready_val[s] = d.ready_value;
     n_sub += (d.nkv + 63) / 64;
+    sh.n_box += (d.nkv + 127) / 128;
   }
   LD_CHECK_ARG(n_sub <= kMaxSub, "ld_attention: %d keys-blocks exceed the limit of %d (131072 keys)", n_sub, kMaxSub);
   sh.n = n_shards;
@@ -949,11 +1112,29 @@ extern "C" int ld_attention_shards_bf16(const void* q, const ld_kv_shard* shards
   prm.q = (const bf16*)q;
   prm.q_rows = q_rows;
   prm.scale_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  const int grid = BH * ((nq + 255) / 256);
+  int grid = BH * ((nq + 255) / 256);
+  prm.n_main = grid;
+  prm.n_split = 1;
+  prm.part_o = prm.part_lse = nullptr;
+  if (variant != 1 && variant != 6 && lse == nullptr && out_f32 == nullptr) {
+    // callers that want the log-sum-exp (ring merges) get one CTA per query block; everyone else the tail split
+    int n_main = grid;
+    const int S = plan_tail_split(grid, sm_count(), sh.n_box, &n_main);
+    const size_t need = (size_t)(grid - n_main) * S * 256 * 65 * sizeof(float);
+    if (S > 1 && workspace != nullptr && workspace_bytes >= need) {   // no workspace: one CTA per query block
+      LD_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "ld_attention: workspace must be 16-byte aligned");
+      prm.part_o = reinterpret_cast<float*>(workspace);
+      prm.part_lse = prm.part_o + (size_t)(grid - n_main) * S * 256 * 64;
+      prm.n_main = n_main;
+      prm.n_split = S;
+      grid = n_main + (grid - n_main) * S;
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   // variant 0: fast path (5 of 16 column pairs on the FMA-pipe polynomial) with the exact path as in-launch fallback
   //         1: exact path only (per-block maxima, lazy rescaling)
   //         2 / 3 / 4: fast path with 0 / 4 / 6 of 16 pairs on the polynomial   5: variant 0 with truncating bf16 pack
+  //         6: variant 0 with one CTA per query block even in the last wave (no tail split)
   switch (variant) {
     case 0:
       if (g_attn_prof != nullptr) {
@@ -968,6 +1149,7 @@ extern "C" int ld_attention_shards_bf16(const void* q, const ld_kv_shard* shards
     case 3: return launch_attn5<4, false>(sh, prm, grid, st);
     case 4: return launch_attn5<6, false>(sh, prm, grid, st);
     case 5: return launch_attn5<5, true>(sh, prm, grid, st);
+    case 6: return launch_attn5<5, false>(sh, prm, grid, st);   // variant 0 without the tail split (A/B, tests)
     default:
       set_error("ld_attention: unknown variant %d", variant);
       return LD_ERR_ARG;

@@ -92,7 +92,10 @@ int ld_gemm_bf16(const ld_gemm_args* args, void* stream);
    variant: 0 = default (one fixed reference maximum per row, 5 of 16 exponential pairs on the FMA pipe, row sums on the
    tensor core; CTAs whose reference overflowed re-run through the exact path inside the same launch), 1 = exact path only
    (per-block maxima, lazy rescaling), 2 / 3 / 4 = default with 0 / 4 / 6 of 16 pairs on the FMA pipe, 5 = default with a
-   truncating bf16 pack (tuning variants).
+   truncating bf16 pack (tuning variants), 6 = default without the tail split.
+   Tail split: the query blocks of the last, partly empty wave of the grid are each served by several CTAs that take a share
+   of the keys and write fp32 partial results, merged by a second small kernel.  It needs a workspace, so it is only
+   available through ld_attention_shards_ws_bf16 (LD_ATTN_SPLIT=0 disables it; it is also off when lse is requested).
    If lse != NULL also writes fp32 log2-sum-exp [BH, nq] and, when out_f32 != NULL, the normalised fp32 output
    [BH, nq, 64].  Replaces SAT attention_fn_default -> F.scaled_dot_product_attention reached through
    dit_video_concat.py:655-664. */
@@ -114,6 +117,14 @@ typedef struct ld_kv_shard {
 } ld_kv_shard;
 int ld_attention_shards_bf16(const void* q, const ld_kv_shard* shards, int n_shards, void* out, float* lse, float* out_f32,
                              int batch, int heads, int nq, int q_rows, int variant, void* stream);
+
+/* The same with a caller-owned workspace for the tail split (see ld_attention_bf16): ld_attention_workspace_bytes says how
+   much this problem wants (0: nothing to split); with workspace == NULL or too small the launch uses one CTA per query
+   block.  The workspace must stay untouched until the launch has finished on `stream`. */
+size_t ld_attention_workspace_bytes(const ld_kv_shard* shards, int n_shards, int batch, int heads, int nq);
+int ld_attention_shards_ws_bf16(const void* q, const ld_kv_shard* shards, int n_shards, void* out, float* lse, float* out_f32,
+                                int batch, int heads, int nq, int q_rows, int variant, void* workspace,
+                                size_t workspace_bytes, void* stream);
 /* copies the per-device status word of the shard waits to *host_out (synchronising); reset != 0 clears it */
 int ld_attention_status(unsigned int* host_out, int reset);
 

@@ -54,6 +54,9 @@ SIGNATURES = {
     "ld_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "ld_attention_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "ld_attention_shards_bf16": (C.c_int, [_vp, C.POINTER(KvShard), _i, _vp, _fp, _fp, _i, _i, _i, _i, _i, _vp]),
+    "ld_attention_workspace_bytes": (C.c_size_t, [C.POINTER(KvShard), _i, _i, _i, _i]),
+    "ld_attention_shards_ws_bf16": (C.c_int, [_vp, C.POINTER(KvShard), _i, _vp, _fp, _fp, _i, _i, _i, _i, _i, _vp, C.c_size_t,
+                                              _vp]),
     "ld_attention_status": (C.c_int, [C.POINTER(C.c_uint), _i]),
     "ld_attention_merge": (C.c_int, [_fp, _fp, _fp, _fp, _vp, _i, _i, _i, _vp]),
     "ld_nchw_to_nhwc": (C.c_int, [_vp, _i, _vp, _i, _i, _i, _vp]),
@@ -85,7 +88,7 @@ def lib_path() -> Path:
     return _build.LIB_PATH
 
 
-ABI_VERSION = 4   # must equal ld_abi_version() of the loaded library (bumped whenever a signature or struct changes)
+ABI_VERSION = 5   # must equal ld_abi_version() of the loaded library (bumped whenever a signature or struct changes)
 
 
 def load() -> C.CDLL:
@@ -122,7 +125,7 @@ class LanDiffB200Error(RuntimeError):
 LAUNCHES = [0]  # KERNELS launched through the C-ABI (every compute entry point launches exactly one kernel)
 # entry points that launch no kernel: queries, allocation, copy-engine copies and stream memory operations
 _NO_KERNEL = {"ld_device_check", "ld_ipc_alloc", "ld_ipc_open", "ld_ipc_close", "ld_ipc_free", "ld_copy_async",
-              "ld_stream_write_u32", "ld_stream_wait_geq_u32", "ld_attention_status", "w"}
+              "ld_stream_write_u32", "ld_stream_wait_geq_u32", "ld_attention_status", "ld_attention_workspace_bytes", "w"}
 
 
 def check(rc: int, what: str) -> None:

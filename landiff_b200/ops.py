@@ -166,9 +166,23 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, nq: Optional
         _chk(out_f32, F32, "out_f32")
         if lse is None or out_f32.numel() != B * H * nq * 64:
             raise ValueError("attention: out_f32 must hold [B*H, nq, 64] elements and needs lse")
-    check(_C.load().ld_attention_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _ptr(lse), _ptr(out_f32),
-                                      B, H, nq, q_rows, nkv, kv_rows, variant, _stream()), "ld_attention_bf16")
+    one = (_C.KvShard * 1)()
+    one[0].k, one[0].v, one[0].nkv, one[0].kv_rows = k.data_ptr(), v.data_ptr(), nkv, kv_rows
+    _attention_launch(q, one, 1, out, lse, out_f32, B, H, nq, q_rows, variant)
     return out
+
+
+def _attention_launch(q, arr, n, out, lse, out_f32, B, H, nq, q_rows, variant) -> None:
+    """One launch through the workspace entry point: the tail split's partial results live in a torch allocation (stream-
+    ordered caching allocator: safe across streams and under CUDA-graph capture)."""
+    lib = _C.load()
+    ws, ws_bytes = None, 0
+    if lse is None and out_f32 is None and variant not in (1, 6):
+        ws_bytes = int(lib.ld_attention_workspace_bytes(arr, n, B, H, nq))
+        if ws_bytes:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+    check(lib.ld_attention_shards_ws_bf16(q.data_ptr(), arr, n, out.data_ptr(), _ptr(lse), _ptr(out_f32), B, H, nq, q_rows,
+                                          variant, _ptr(ws), ws_bytes, _stream()), "ld_attention_shards_ws_bf16")
 
 
 def attention_shards(q: torch.Tensor, shards, *, nq: Optional[int] = None, out: Optional[torch.Tensor] = None,
@@ -214,8 +228,7 @@ def attention_shards(q: torch.Tensor, shards, *, nq: Optional[int] = None, out: 
         _chk(out_f32, F32, "out_f32")
         if lse is None or out_f32.numel() != B * H * nq * 64:
             raise ValueError("attention: out_f32 must hold [B*H, nq, 64] elements and needs lse")
-    check(_C.load().ld_attention_shards_bf16(q.data_ptr(), arr, len(shards), out.data_ptr(), _ptr(lse), _ptr(out_f32),
-                                             B, H, nq, q_rows, variant, _stream()), "ld_attention_shards_bf16")
+    _attention_launch(q, arr, len(shards), out, lse, out_f32, B, H, nq, q_rows, variant)
     return out
 
 

@@ -208,6 +208,47 @@ def test_attention_over_kv_shards_equals_monolithic(variant):
                 assert torch.equal(mono, out), f"shards {lens}: differs from the monolithic launch"
 
 
+def test_attention_tail_split():
+    """Tail split (wave quantisation): without an lse request, the query blocks of the last, partly empty wave are served by
+    several CTAs that each take a share of the key boxes and write fp32 partial results, merged by a second kernel.  Shapes:
+    a grid with full waves + a tail (160 blocks), grids smaller than one wave (every block is split, up to 16 ways), key
+    ranges that cross ragged shard boundaries, and an overflowing key inside ONE split (exact-path redo of a split CTA).
+    Variant 6 is the same kernel with one CTA per query block."""
+    torch.manual_seed(11)
+    for (B, H, nq, lens) in [(1, 10, 4000, (4000,)), (1, 4, 4444, (17776,)), (1, 2, 500, (4444, 4444, 4444, 4444)),
+                             (1, 3, 700, (1000, 129, 65, 2000)), (2, 2, 300, (1537,))]:
+        nkv = sum(lens)
+        q = torch.randn(B, H, nq, 64, device=dev).bfloat16()
+        k = torch.randn(B, H, nkv, 64, device=dev).bfloat16()
+        v = torch.randn(B, H, nkv, 64, device=dev).bfloat16()
+        shards, o = [], 0
+        for n in lens:
+            shards.append((k[:, :, o:o + n].contiguous(), v[:, :, o:o + n].contiguous(), n))
+            o += n
+        out = ops.attention_shards(q, shards)                 # variant 0: tail split where the plan finds one
+        plain = ops.attention_shards(q, shards, variant=6)
+        torch.cuda.synchronize()
+        ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+        ref = ref.permute(0, 2, 1, 3).reshape(B, nq, H * 64)
+        report(f"attn tail split B{B} H{H} nq{nq} {lens}", out, ref)
+        report("   no split", plain, ref)
+        assert (out.float() - plain.float()).abs().max().item() < 2e-2
+        assert torch.equal(out, ops.attention_shards(q, shards)), "tail split is not reproducible"
+    # an overflowing key inside one split: that split's CTAs re-run through the exact path and still write partials
+    B, H, nq, nkv = 1, 2, 1000, 3000
+    q = torch.randn(B, H, nq, 64, device=dev)
+    k = torch.randn(B, H, nkv, 64, device=dev)
+    v = torch.randn(B, H, nkv, 64, device=dev).bfloat16()
+    q[..., 0] = q[..., 0].abs() + 3.0
+    k[:, :, 2500, :] = 0
+    k[:, :, 2500, 0] = 400.0
+    q, k = q.bfloat16(), k.bfloat16()
+    out = ops.attention(q, k, v)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    report("attn tail split + overflow", out, ref.permute(0, 2, 1, 3).reshape(B, nq, H * 64))
+
+
 def test_attention_shard_arrival_flags():
     """A shard guarded by an arrival flag is not read before the flag reaches the expected value: the flag is raised by
     a stream memory operation on a SECOND stream after a delay and a late fill of the buffer; without the in-kernel wait
