@@ -280,7 +280,7 @@ def run_ours(args):
         # of the shipped kernel at the same shape and B = 1 (read from profiles/r2_ncu_attn5.csv); the launch is
         # independent per batch row, so B rows move B times that.  Algorithmic bytes (Q, K, V in, O out) = 273 MB per
         # row: K/V re-reads of the 70 query blocks of a head are served by L2.  Sequence-parallel shards: no capture.
-        traffic, traffic_src = None, None
+        traffic, traffic_src = None, "no ncu capture at the sequence-parallel shard shape"
         if layout.sp_size == 1:
             traffic, traffic_src = ncu_dram_bytes(ROOT / "profiles" / "r2_ncu_attn5.csv", "attn5_kernel")
             traffic = traffic * b_rows if traffic is not None else None
@@ -297,7 +297,7 @@ def run_ours(args):
                        "weights": "seeded random init N(0, 0.02^2)", "sampler_steps_per_video": SAMPLER_STEPS},
             "tensor_frac_of_peak_whole_step": round(FLOP_PER_CFG_STEP_FULL / (ms_per_step * 1e-3) / world / 1e12 / tf_peak, 4),
             "roofline": {"bound": "tensor", "kernel": "attn5_kernel (tcgen05 flash attention, head_dim 64: double-buffered scores, 16 softmax warps, Q in "
-                                   "TMEM, P in place over S, row sums on the tensor core, 5/16 exponential pairs on the FMA pipe"
+                                   "TMEM, P in place over S, row sums on the tensor core, 5/16 exponential pairs on the FMA pipe, last partial wave split over key ranges"
                                    + ("" if layout.sp_size == 1 else f"; one launch over {layout.sp_size} K/V shards, arrival flags polled in-kernel") + ")",
                          "achieved": round(achieved, 1), "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": round(achieved / tf_peak, 4), "traffic": traffic,
