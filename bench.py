@@ -297,7 +297,7 @@ def run_ours(args):
                        "weights": "seeded random init N(0, 0.02^2)", "sampler_steps_per_video": SAMPLER_STEPS},
             "tensor_frac_of_peak_whole_step": round(FLOP_PER_CFG_STEP_FULL / (ms_per_step * 1e-3) / world / 1e12 / tf_peak, 4),
             "roofline": {"bound": "tensor", "kernel": "attn5_kernel (tcgen05 flash attention, head_dim 64: double-buffered scores, 16 softmax warps, Q in "
-                                   "TMEM, P in place over S, row sums on the tensor core, 5/16 exponential pairs on the FMA pipe, last partial wave split over key ranges"
+                                   "TMEM, P in place over S, row sums on the tensor core, 4/16 exponential pairs on the FMA pipe, last partial wave split over key ranges"
                                    + ("" if layout.sp_size == 1 else f"; one launch over {layout.sp_size} K/V shards, arrival flags polled in-kernel") + ")",
                          "achieved": round(achieved, 1), "peak": tf_peak, "unit": "TFLOP/s",
                          "frac": round(achieved / tf_peak, 4), "traffic": traffic,

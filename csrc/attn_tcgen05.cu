@@ -30,6 +30,11 @@ constexpr int kMaxShards = 4;
 constexpr int kMaxSub = 2048;                // 64-key sub-blocks per launch: up to 131 072 keys over all shards
 constexpr int kKS = 4;                       // K and V ring depth (128-key boxes)
 constexpr int kAttnThreads = 640;
+// Exponential pairs (of 16) on the FMA-pipe polynomial in the default variant.  In isolation (boost clock) 5 is the fastest;
+// inside a sampler step the board runs at its power cap (~1.6 GHz) and the polynomial's extra FMA-pipe work costs clock:
+// measured in-step 374.7 ms/step with 4 against 380.7 with 5 (profiles/r2_attn_kp_in_step.txt), sustained back-to-back
+// launches 5.30 / 5.37 / 5.50 / 6.07 ms for 4 / 3 / 5 / 6 (profiles/r2_attn_sustained_bench.txt).
+constexpr int kDefaultKP = 4;
 
 struct alignas(64) AttnShards {
   CUtensorMap q;                         // [64, nq, BH], box 64 x 128 (exact path)
@@ -1131,25 +1136,33 @@ extern "C" int ld_attention_shards_ws_bf16(const void* q, const ld_kv_shard* sha
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
-  // variant 0: fast path (5 of 16 column pairs on the FMA-pipe polynomial) with the exact path as in-launch fallback
+  // variant 0: fast path (4 of 16 column pairs on the FMA-pipe polynomial) with the exact path as in-launch fallback
   //         1: exact path only (per-block maxima, lazy rescaling)
-  //         2 / 3 / 4: fast path with 0 / 4 / 6 of 16 pairs on the polynomial   5: variant 0 with truncating bf16 pack
+  //         2 / 3 / 4: fast path with 0 / 5 / 6 of 16 pairs on the polynomial   5: variant 0 with truncating bf16 pack
   //         6: variant 0 with one CTA per query block even in the last wave (no tail split)
+  // share of exponential pairs on the FMA-pipe polynomial for the default variants (0, 6): LD_ATTN_KP = 2..6 (A/B switch)
+  static const int kp_default = [] { const char* e = getenv("LD_ATTN_KP"); const int v = e ? atoi(e) : 0; return (v >= 2 && v <= 6) ? v : kDefaultKP; }();
   switch (variant) {
     case 0:
-      if (g_attn_prof != nullptr) {
+    case 6:   // 6: variant 0 with one CTA per query block even in the last wave (no tail split)
+      if (g_attn_prof != nullptr && variant == 0) {
         prm.prof = g_attn_prof;
-        return launch_attn5<5, false, true>(sh, prm, grid, st);
+        return launch_attn5<kDefaultKP, false, true>(sh, prm, grid, st);
       }
-      return launch_attn5<5, false>(sh, prm, grid, st);
+      switch (kp_default) {
+        case 2: return launch_attn5<2, false>(sh, prm, grid, st);
+        case 3: return launch_attn5<3, false>(sh, prm, grid, st);
+        case 6: return launch_attn5<6, false>(sh, prm, grid, st);
+        case 5: return launch_attn5<5, false>(sh, prm, grid, st);
+        default: return launch_attn5<4, false>(sh, prm, grid, st);
+      }
     case 1:
       prm.exact_only = 1;
       return launch_attn5<5, false>(sh, prm, grid, st);
     case 2: return launch_attn5<0, false>(sh, prm, grid, st);
-    case 3: return launch_attn5<4, false>(sh, prm, grid, st);
+    case 3: return launch_attn5<5, false>(sh, prm, grid, st);
     case 4: return launch_attn5<6, false>(sh, prm, grid, st);
-    case 5: return launch_attn5<5, true>(sh, prm, grid, st);
-    case 6: return launch_attn5<5, false>(sh, prm, grid, st);   // variant 0 without the tail split (A/B, tests)
+    case 5: return launch_attn5<kDefaultKP, true>(sh, prm, grid, st);
     default:
       set_error("ld_attention: unknown variant %d", variant);
       return LD_ERR_ARG;

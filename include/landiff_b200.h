@@ -89,9 +89,9 @@ int ld_gemm_bf16(const ld_gemm_args* args, void* stream);
 /* ---- full (non-causal) self-attention, head_dim 64, flash-style online softmax on tcgen05 ------------- */
 /* q: [BH, q_rows, 64], k/v: [BH, kv_rows, 64] bf16; scores are scaled by 1/sqrt(64) inside the kernel.
    Uses q rows [0,nq) and kv rows [0,nkv).  out: bf16 [B, nq, heads*64] (token-major, ready for `dense`).
-   variant: 0 = default (one fixed reference maximum per row, 5 of 16 exponential pairs on the FMA pipe, row sums on the
+   variant: 0 = default (one fixed reference maximum per row, 4 of 16 exponential pairs on the FMA pipe, row sums on the
    tensor core; CTAs whose reference overflowed re-run through the exact path inside the same launch), 1 = exact path only
-   (per-block maxima, lazy rescaling), 2 / 3 / 4 = default with 0 / 4 / 6 of 16 pairs on the FMA pipe, 5 = default with a
+   (per-block maxima, lazy rescaling), 2 / 3 / 4 = default with 0 / 5 / 6 of 16 pairs on the FMA pipe, 5 = default with a
    truncating bf16 pack (tuning variants), 6 = default without the tail split.
    Tail split: the query blocks of the last, partly empty wave of the grid are each served by several CTAs that take a share
    of the keys and write fp32 partial results, merged by a second small kernel.  It needs a workspace, so it is only

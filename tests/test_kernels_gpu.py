@@ -126,7 +126,7 @@ def test_attention_overflow_fixup(variant):
     """One late key whose score is hundreds of log2-units above every row's first-block maximum: the fixed reference
     maximum of the fast path overflows (on MUFU columns: +inf; on polynomial columns: the clamped exponent field 255) and
     the CTA re-runs its rows through the exact path inside the same launch.  Rows with a negative projection on that key
-    never overflow (mixed flagged / unflagged CTAs).  The key sits on column 2500 % 64 = 4 (pair 2: MUFU for KP = 5,
+    never overflow (mixed flagged / unflagged CTAs).  The key sits on column 2500 % 64 = 4 (pair 2: MUFU for KP = 4,
     polynomial for none); a second run moves it to a polynomial column."""
     torch.manual_seed(5)
     B, H, nq, nkv = 1, 2, 1000, 3000
@@ -137,7 +137,7 @@ def test_attention_overflow_fixup(variant):
     q[:, 1, :300, 0] = -(q[:, 1, :300, 0].abs() + 3.0)  # head 1: first 300 rows never do, the rest do
     q[:, 1, 300:, 0] = q[:, 1, 300:, 0].abs() + 3.0
     q, v = q.bfloat16(), v.bfloat16()
-    for key in (2500, 2496, 2561):     # columns 4 (MUFU pair for KP = 5), 0 (polynomial pair), 1 (second lane of a polynomial pair)
+    for key in (2500, 2496, 2561):     # columns 4 (MUFU pair for KP = 4), 0 (polynomial pair), 1 (second lane of a polynomial pair)
         kk = k.clone()
         kk[:, :, key, :] = 0
         kk[:, :, key, 0] = 400.0
