@@ -162,7 +162,7 @@ int make_tmap_im2col3x3_bf16(CUtensorMap* out, const void* gptr, int C, int W, i
 extern "C" {
 
 const char* ld_last_error(void) { return ld::g_err; }
-int ld_abi_version(void) { return 5; }
+int ld_abi_version(void) { return 6; }
 int ld_device_check(int* sms) {
   int rc = ld::check_device();
   if (rc == LD_OK && sms) *sms = ld::sm_count();

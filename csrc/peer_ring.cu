@@ -42,7 +42,16 @@ extern "C" int ld_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char handle_o
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
   void* p = nullptr;
   LD_CHECK_CUDA(cudaMalloc(&p, bytes));
-  cudaError_t e = cudaMemset(p, 0, bytes);
+  // Zero the buffer (the flag words start at 0) and make sure the zeroing HAS HAPPENED before the handle leaves this
+  // function: cudaMemset on device memory is asynchronous to the host and runs on the legacy default stream — torch's
+  // compute stream — i.e. behind every kernel already queued there.  A peer that maps the buffer and raises a flag in the
+  // meantime would have its flag wiped when the memset finally executes (seen as a lost arrival under load).  A private
+  // non-blocking stream keeps the wait independent of whatever the compute stream is doing (e.g. a kernel polling a flag).
+  cudaStream_t zs = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&zs, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMemsetAsync(p, 0, bytes, zs);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(zs);
+  if (zs != nullptr) cudaStreamDestroy(zs);
   cudaIpcMemHandle_t h;
   if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
   if (e != cudaSuccess) {

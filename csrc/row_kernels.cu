@@ -740,6 +740,45 @@ extern "C" int ld_timestep_embedding(const float* t, float* out, int batch, int 
   return LD_OK;
 }
 
+// Token-major output blocks -> latent layout: out[row, t, c, 2h+p, 2w+q] = block[i, c*4 + p*2 + q] for image token
+// g = g0 + i = (t, h, w).  One thread per (token, column pair): a 4-byte read, a 4-byte store.
+__global__ void __launch_bounds__(256) unpatchify_blocks_kernel(const ld_token_blocks blk, bf16* __restrict__ out, int T, int Hp,
+                                                                int Wp, int C) {
+  const int b = blockIdx.y;
+  const int64_t total = (int64_t)blk.count[b] * 32;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(blk.ptr[b]);
+  const int hw = Hp * Wp, H = 2 * Hp, W = 2 * Wp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int tok = (int)(i >> 5), cp = (int)(i & 31);   // column pair: columns 2cp, 2cp+1  ->  c = cp/2, p = cp%2, q = 0, 1
+    const int g = blk.g0[b] + tok;
+    const int t = g / hw, rem = g - t * hw;
+    const int h = rem / Wp, w = rem - h * Wp;
+    const int c = cp >> 1, pp = cp & 1;
+    const int64_t idx = ((((int64_t)blk.row[b] * T + t) * C + c) * H + (2 * h + pp)) * W + 2 * w;
+    *reinterpret_cast<uint32_t*>(out + idx) = src[i];
+  }
+}
+
+extern "C" int ld_unpatchify_blocks(const ld_token_blocks* blocks, void* out, int T, int Hp, int Wp, int C, void* stream) {
+  int rc = check_device();
+  if (rc != LD_OK) return rc;
+  LD_CHECK_ARG(blocks && out && T > 0 && Hp > 0 && Wp > 0, "ld_unpatchify_blocks: bad arguments");
+  LD_CHECK_ARG(C == 16, "ld_unpatchify_blocks: C=%d (blocks are 64 = 16 x 2 x 2 columns wide)", C);
+  LD_CHECK_ARG(blocks->n >= 1 && blocks->n <= 16, "ld_unpatchify_blocks: 1..16 blocks, got %d", blocks->n);
+  int max_count = 0;
+  for (int b = 0; b < blocks->n; ++b) {
+    LD_CHECK_ARG(blocks->ptr[b] != nullptr && blocks->count[b] >= 0 && blocks->g0[b] >= 0 &&
+                     blocks->g0[b] + blocks->count[b] <= T * Hp * Wp && blocks->row[b] >= 0,
+                 "ld_unpatchify_blocks: bad block %d", b);
+    max_count = blocks->count[b] > max_count ? blocks->count[b] : max_count;
+  }
+  if (max_count == 0) return LD_OK;
+  const dim3 grid(grid_for((int64_t)max_count * 32, 256, sm_count() * 4), blocks->n);
+  unpatchify_blocks_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*blocks, (bf16*)out, T, Hp, Wp, C);
+  LD_CHECK_CUDA(cudaGetLastError());
+  return LD_OK;
+}
+
 extern "C" int ld_sampler_update(const float* x, const void* net_u, const void* net_c, const float* old_den,
                                  const float* eps, float* x_out, float* den_out, int64_t n, float c_skip, float c_out,
                                  float cfg, float m1, float m2, float m3, float m4, float mn, int mode, int net_is_f32,

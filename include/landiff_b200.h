@@ -186,6 +186,18 @@ int ld_small_linear_batched(const float* x, const void* const* Ws, const void* c
 int ld_timestep_embedding(const float* t, float* out, int batch, int dim, float max_period, int round_bf16,
                           void* stream);
 
+/* Token-major network outputs -> latent layout.  Under CFG / sequence parallelism every rank produces the final linear's
+   output for its own (batch row, image-token shard) as a contiguous bf16 [count, 64] block (LD_EPI_BIAS), the blocks travel
+   to every rank by copy-engine peer copies (landiff_b200/dma_ring.py), and this kernel scatters up to 16 of them into
+   out [rows, T, C, 2*Hp, 2*Wp]: block b covers image tokens [g0, g0 + count) of output row `row` (unpatchify,
+   dit_video_concat.py:392-410).  Replaces the zero-fill + mask + all-reduce assembly; the reference has no parallelism. */
+typedef struct ld_token_blocks {
+  const void* ptr[16];
+  int32_t row[16], g0[16], count[16];
+  int32_t n;
+} ld_token_blocks;
+int ld_unpatchify_blocks(const ld_token_blocks* blocks, void* out, int T, int Hp, int Wp, int C, void* stream);
+
 /* fused denoiser scaling + CFG + DPM-Solver++(2M) SDE update, all fp32, n elements:
      den_u = c_out*net_u + c_skip*x ; den_c likewise        (denoiser.py:38-41, denoiser_scaling.py:62-70)
      den   = den_u + cfg*(den_c - den_u)                     (guiders.py:75-79, sampling_utils.py:8-13)

@@ -38,6 +38,13 @@ class GemmArgs(C.Structure):
     ]
 
 
+class TokenBlocks(C.Structure):
+    """Mirror of `ld_token_blocks` (include/landiff_b200.h)."""
+
+    _fields_ = [("ptr", C.c_void_p * 16), ("row", C.c_int32 * 16), ("g0", C.c_int32 * 16), ("count", C.c_int32 * 16),
+                ("n", C.c_int32)]
+
+
 class KvShard(C.Structure):
     """Mirror of `ld_kv_shard` (include/landiff_b200.h)."""
 
@@ -65,6 +72,7 @@ SIGNATURES = {
     "ld_im2col3x3": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _fp, _vp, _vp, _i, _i, _vp]),
     "ld_pixel_shuffle2": (C.c_int, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "ld_conv3x3_to_nchw16": (C.c_int, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ld_unpatchify_blocks": (C.c_int, [C.POINTER(TokenBlocks), _vp, _i, _i, _i, _i, _vp]),
     "ld_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]),
     "ld_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "ld_ipc_close": (C.c_int, [_vp]),
@@ -88,7 +96,7 @@ def lib_path() -> Path:
     return _build.LIB_PATH
 
 
-ABI_VERSION = 5   # must equal ld_abi_version() of the loaded library (bumped whenever a signature or struct changes)
+ABI_VERSION = 6   # must equal ld_abi_version() of the loaded library (bumped whenever a signature or struct changes)
 
 
 def load() -> C.CDLL:

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._C import EPI_BIAS_GELU, EPI_BIAS_POS, EPI_GATED_RESID, EPI_NONE, EPI_QKV, EPI_UNPATCHIFY
+from ._C import EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_POS, EPI_GATED_RESID, EPI_NONE, EPI_QKV, EPI_UNPATCHIFY
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -321,6 +321,10 @@ class DiffusionTransformer(nn.Module):
             ws["fmod"] = e(B, 2 * d, dt=F32)
             ws["fin"] = e(B * max(ws["n_img"], 1), d)
             ws["out"] = e(B, T, self.out_channels, H, W)
+            # token-major output for the peer-copy exchange (landiff_b200/parallel.py OutputGather): every rank's block has
+            # the size of the largest shard so that one fixed-size copy moves it
+            ws["tok_rows"] = (n_total + max(self.sp_layout.sp_size, 1) - 1) // max(self.sp_layout.sp_size, 1) if self.sp_layout else R
+            ws["tok_out"] = e(B, ws["tok_rows"], self.out_channels * 4)
         self._ws[key] = ws
         return ws
 
@@ -424,6 +428,12 @@ class DiffusionTransformer(nn.Module):
         ops.final_norm_modulate(ws["hidden"].view(B * R, d), fln.weight, fln.bias, BLOCK_LAYERNORM_EPS,
                                 fl.norm_final.weight, fl.norm_final.bias, FINAL_NORM_EPS, ws["fmod"][:, :d],
                                 ws["fmod"][:, d:], 2 * d, B, R, ws["shard"].start, TL, out=ws["fin"])
+        if getattr(self, "token_major_out", False):
+            # sequence / CFG parallel: the (row, token shard) block stays token-major [B, tok_rows, 64] (rows [0, n_img) valid);
+            # parallel.OutputGather ships it to every rank and unpatchifies there
+            ops.gemm(ws["fin"], fl.linear.weight, epilogue=EPI_BIAS, bias=fl.linear.bias,
+                     out=ws["tok_out"].view(B * ws["tok_rows"], -1), rows_per_batch=ws["n_img"], out_rows_per_batch=ws["tok_rows"])
+            return ws["tok_out"]
         ops.gemm(ws["fin"], fl.linear.weight, epilogue=EPI_UNPATCHIFY, bias=fl.linear.bias, out=ws["out"],
                  rows_per_batch=ws["n_img"], tok_offset=TL + ws["g0"], text_len=TL,
                  patch_grid=(T, H // 2, W // 2, self.out_channels))

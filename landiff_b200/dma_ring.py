@@ -29,7 +29,7 @@ import torch.distributed as dist
 from . import _C
 from .ops import check
 
-FLAG_BYTES = 256   # ready[slot] (u32) at 4 * slot, free[slot] at 128 + 4 * slot; slot < 8
+FLAG_BYTES = 256   # ready[slot] (u32) at 4 * slot, free[slot] at 128 + 4 * slot; slot < 32
 FREE_OFF = 128
 
 
@@ -59,12 +59,12 @@ class PeerGather:
     csrc/attn_tcgen05.cu).  Slot numbering: on rank r the shard of source s lives in recv[((r - s) % n) - 1], i.e. slot
     j - 1 holds the shard of rank r - j — the j-th shard the attention kernel consumes after the local one."""
 
-    def __init__(self, group, group_ranks: List[int], my_rank: int, shard_shape, dtype, device):
+    def __init__(self, group, group_ranks: List[int], my_rank: int, shard_shape, dtype, device, max_ranks: int = 4):
         self.lib = _C.load()
         self.device = device
         n = len(group_ranks)
-        if not 2 <= n <= 4:
-            raise ValueError(f"sequence-parallel groups of 2..4 ranks are supported, got {n}")
+        if not 2 <= n <= max_ranks or max_ranks > 32:   # the flag page holds 32 ready + 32 free words
+            raise ValueError(f"groups of 2..{max_ranks} ranks are supported, got {n}")
         self.n = n
         self.me = group_ranks.index(my_rank)
         self.nbytes = int(torch.empty(shard_shape, dtype=dtype, device="meta").numel()) * torch.empty((), dtype=dtype).element_size()
@@ -120,6 +120,16 @@ class PeerGather:
             buf = self.recv[j - 1]
             out.append((buf[0], buf[1], None, self._flags_ptr + 4 * (j - 1), T))
         return out
+
+    def wait_all(self, T: int, stream) -> None:
+        """Enqueue on `stream`: stream-level waits (no kernel) until every source's transfer T has landed — for consumers
+        that are plain kernels (the attention kernel polls the flags itself instead)."""
+        for j in range(1, self.n):
+            check(self.lib.ld_stream_wait_geq_u32(self._flags_ptr + 4 * (j - 1), T, stream.cuda_stream), "ld_stream_wait_geq_u32")
+
+    def source_rank_of_slot(self, j: int) -> int:
+        """Index (within the group) of the rank whose block sits in recv[j - 1]: the rank at distance j upstream."""
+        return (self.me - j) % self.n
 
     def release_all(self, T: int, stream) -> None:
         """Enqueue on `stream` (after the attention kernel that read the receive buffers): tell every source its shard

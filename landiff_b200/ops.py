@@ -300,6 +300,30 @@ def patchify(x: torch.Tensor, sem: Optional[torch.Tensor], g0: int = 0, n: Optio
     return out
 
 
+def unpatchify_blocks(blocks, out: torch.Tensor) -> torch.Tensor:
+    """Scatter token-major bf16 [count, 64] blocks into the latent layout out [rows, T, 16, H, W].  `blocks`: sequence of
+    (tensor or device address, row, g0, count) — block covers image tokens [g0, g0 + count) of output row `row`."""
+    _chk(out, BF16, "out")
+    if out.dim() != 5 or out.shape[2] != 16 or out.shape[3] % 2 or out.shape[4] % 2:
+        raise ValueError("unpatchify_blocks: out must be [rows, T, 16, H, W] with even H, W")
+    if not 1 <= len(blocks) <= 16:
+        raise ValueError(f"unpatchify_blocks: 1..16 blocks, got {len(blocks)}")
+    rows, T, Cc, H, W = out.shape
+    tb = _C.TokenBlocks()
+    for i, (src, row, g0, count) in enumerate(blocks):
+        if isinstance(src, torch.Tensor):
+            _chk(src, BF16, "block")
+            if src.numel() < count * 64:
+                raise ValueError("unpatchify_blocks: block tensor smaller than count x 64")
+            src = src.data_ptr()
+        if not (0 <= row < rows and g0 >= 0 and count >= 0 and g0 + count <= T * (H // 2) * (W // 2)):
+            raise ValueError(f"unpatchify_blocks: block {i} (row {row}, tokens [{g0}, {g0 + count})) outside the output")
+        tb.ptr[i], tb.row[i], tb.g0[i], tb.count[i] = int(src), int(row), int(g0), int(count)
+    tb.n = len(blocks)
+    check(_C.load().ld_unpatchify_blocks(C.byref(tb), out.data_ptr(), T, H // 2, W // 2, Cc, _stream()), "ld_unpatchify_blocks")
+    return out
+
+
 def small_linear(x, w, bias, act_in=0, act_out=0, round_bf16=True, out=None):
     _chk(x, F32, "x")
     _chk(w, BF16, "w")
@@ -558,6 +582,7 @@ def register_torch_ops() -> None:
     D("pixel_shuffle2(Tensor x) -> Tensor")
     D("conv3x3_to_nchw16(Tensor x, Tensor w, Tensor? bias) -> Tensor")
     D("linear_bias_add(Tensor a, Tensor w, Tensor? bias, Tensor add) -> Tensor")
+    D("unpatchify_blocks(Tensor[] blocks, int[] rows, int[] g0, int[] counts, Tensor(a!) out) -> ()")
 
     def _im2col3x3(x, gn_stats, gamma, beta, groups=32, swish=True):
         gn = None if gn_stats is None else (gn_stats, gamma, beta, groups)
@@ -630,7 +655,9 @@ def register_torch_ops() -> None:
                      ("conv3x3", lambda x, w_taps, bias, add: conv3x3(x, w_taps, bias, add=add)),
                      ("pixel_shuffle2", lambda x: pixel_shuffle2(x)),
                      ("conv3x3_to_nchw16", lambda x, w, bias: conv3x3_to_nchw16(x, w, bias)),
-                     ("linear_bias_add", _linear_bias_add)):
+                     ("linear_bias_add", _linear_bias_add),
+                     ("unpatchify_blocks", lambda blocks, rows, g0, counts, out:
+                      (unpatchify_blocks(list(zip(blocks, rows, g0, counts)), out), None)[1])):
         lib.impl(name, fn, "CUDA")
     register_torch_ops._lib = lib  # keep alive
     _registered = True
@@ -639,6 +666,6 @@ def register_torch_ops() -> None:
 TORCH_OPS = ("attention", "attention_lse", "attention_merge", "linear", "linear_gated_residual", "linear_qkv",
              "linear_bias_pos", "linear_unpatchify", "layernorm_modulate", "final_norm_modulate", "patchify", "small_linear",
              "small_linear_batched", "timestep_embedding", "sampler_update", "nchw_to_nhwc", "groupnorm_stats", "groupnorm_apply", "conv3x3", "im2col3x3",
-             "pixel_shuffle2", "conv3x3_to_nchw16", "linear_bias_add")
+             "pixel_shuffle2", "conv3x3_to_nchw16", "linear_bias_add", "unpatchify_blocks")
 
 register_torch_ops()

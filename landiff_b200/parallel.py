@@ -184,6 +184,60 @@ def _all_reduce_sum(buf: torch.Tensor, group) -> None:
         dist.all_reduce(buf, group=group)
 
 
+class OutputGather:
+    """Exchange of the network outputs under CFG / sequence parallelism without an all-reduce: every rank's final linear
+    leaves its (batch row, image-token shard) block token-major in a fixed-size buffer; the copy engines push it into an
+    IPC-mapped receive buffer on every other rank (the same `PeerGather` protocol as the K|V exchange: monotonically
+    increasing transfer ids, ready / free flags, no SMs, no host synchronisation); each rank then waits for the arrival
+    flags with stream memory operations and ONE small kernel scatters all blocks into the latent layout
+    (`ops.unpatchify_blocks`).  Replaces zero-fill + mask + a 4.5 MB all-reduce (1.1 ms on 8 GPUs) per sampler step."""
+
+    def __init__(self, layout: Layout, world_group, device, rows_local: int, tok_rows: int):
+        from .dma_ring import PeerGather
+
+        self.layout = layout
+        self.rows_local, self.tok_rows = rows_local, tok_rows
+        self.pg = PeerGather(world_group, list(range(layout.world)), layout.rank, (rows_local, tok_rows, 64),
+                             torch.bfloat16, device, max_ranks=16)
+        self.comm_stream = torch.cuda.Stream(device=device, priority=-1)
+        self._sent = None     # event: the previous push has read the send buffer
+
+    def blocks_of(self, rank: int, base, n_total: int, text_len: int):
+        """(address, row, g0, count) of the blocks inside rank `rank`'s buffer at `base` (a tensor or a device address)."""
+        lay = self.layout
+        s = rank % lay.sp_size
+        start, count = shard_bounds(n_total, lay.sp_size, s)
+        g0 = max(start - text_len, 0)
+        n_img = start + count - max(start, text_len)
+        addr = base.data_ptr() if isinstance(base, torch.Tensor) else int(base)
+        rows = [rank // lay.sp_size] if lay.cfg_size == 2 else list(range(self.rows_local))
+        return [(addr + i * self.tok_rows * 64 * 2, r, g0, n_img) for i, r in enumerate(rows)]
+
+    def gather(self, tok_local: torch.Tensor, out: torch.Tensor, n_total: int, text_len: int) -> torch.Tensor:
+        """tok_local: this rank's [rows_local, tok_rows, 64] block (persistent buffer); out: [2, T, 16, H, W] bf16."""
+        assert tuple(tok_local.shape) == (self.rows_local, self.tok_rows, 64) and tok_local.is_contiguous()
+        compute = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(compute)                       # the final GEMM has written the block
+        self.comm_stream.wait_event(ready)
+        T = self.pg.push_all(tok_local, self.comm_stream)
+        self._sent = torch.cuda.Event()
+        self._sent.record(self.comm_stream)
+        blocks = self.blocks_of(self.layout.rank, tok_local, n_total, text_len)
+        for j in range(1, self.pg.n):
+            blocks += self.blocks_of(self.pg.source_rank_of_slot(j), self.pg.recv[j - 1], n_total, text_len)
+        self.pg.wait_all(T, compute)
+        from . import ops
+
+        ops.unpatchify_blocks(blocks, out)
+        self.pg.release_all(T, compute)
+        compute.wait_event(self._sent)              # the next step's final GEMM overwrites tok_local
+        return out
+
+    def close(self):
+        self.pg.close()
+
+
 class CFGGroup:
     """Evaluates one CFG batch row per half of the ranks and exchanges the bf16 outputs (and, under sequence
     parallelism, assembles the token shards) with ONE all-reduce over all ranks: every rank writes its
@@ -192,6 +246,18 @@ class CFGGroup:
     def __init__(self, layout: Layout, world_group=None):
         self.layout, self.group = layout, world_group
         self._buf = None
+        self._gather = None   # OutputGather, created on the first token-major network output
+
+    def _gather_tokens(self, network, net: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        """net: the network's token-major block [rows_local, tok_rows, 64] (see DiffusionTransformer._final)."""
+        m = network.main_model.diffusion_model if hasattr(network, "main_model") else network
+        n_total = m.text_length + x.shape[1] * (x.shape[3] // 2) * (x.shape[4] // 2)
+        if self._gather is None:
+            self._gather = OutputGather(self.layout, self.group, x.device, net.shape[0], net.shape[1])
+        shape = (2,) + tuple(x.shape[1:])
+        if self._buf is None or self._buf.shape != shape or self._buf.dtype != torch.bfloat16:
+            self._buf = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+        return self._gather.gather(net, self._buf, n_total, m.text_length)
 
     def my_row(self) -> int:
         return self.layout.cfg_rank if self.layout.cfg_size == 2 else -1
@@ -217,11 +283,17 @@ class CFGGroup:
             row = lay.cfg_rank
             t1 = torch.full((1,), timestep, dtype=torch.float32, device=x.device)
             net = network(x, t1, {"crossattn": ctx2[row:row + 1]}, idx=t1, **kwargs)
+            if net.dim() == 3:        # token-major block: peer-copy exchange instead of the all-reduce
+                buf = self._gather_tokens(network, net, x)
+                return buf[0:1], buf[1:2]
             mask = getattr(network, "owned_latent_mask", None)
             buf = self.assemble(net, row, mask(x) if mask is not None else None)
             return buf[0:1], buf[1:2]
         t2 = torch.full((2,), timestep, dtype=torch.float32, device=x.device)
         net = network(torch.cat([x, x]), t2, {"crossattn": ctx2}, idx=t2, **kwargs)
+        if net.dim() == 3:
+            buf = self._gather_tokens(network, net, x)
+            return buf[0:1], buf[1:2]
         if lay.sp_size > 1:
             # ring SP without CFG parallelism: both rows live here, but only this rank's token shard of each was written
             mask = getattr(network, "owned_latent_mask", None)
@@ -257,6 +329,12 @@ def attach(warp, layout: Layout, sp_group, device) -> None:
         m = wrapper.diffusion_model
         m.ring = RingAttention(layout, sp_group, device)
         m.sp_layout = layout
+    # with the copy-engine transport the network output is exchanged the same way (CFGGroup -> OutputGather): the final
+    # linear leaves its block token-major; LD_OUTPUT_EXCHANGE=allreduce keeps the all-reduce assembly (A/B, NCCL-only setups)
+    import os
+
+    if warp.main_model.diffusion_model.ring.transport == "dma" and os.environ.get("LD_OUTPUT_EXCHANGE", "dma") == "dma":
+        warp.main_model.diffusion_model.token_major_out = True
 
     def mask_fn(x):
         m = warp.main_model.diffusion_model

@@ -108,10 +108,18 @@ def check_network(layout, sp_group, dev, transport):
         if m.ring is not None:
             for pg in m.ring._peer.values():
                 pg.close()
+    if layout.sp_size > 1 and transport == "dma":
+        assert grp._gather is not None, "the copy-engine output exchange was not used"
+    if grp._gather is not None:
+        grp._gather.close()
     return max(r_u, r_c), r_t, status
 
 
 def main():
+    import faulthandler
+
+    # a rank stuck in a collective or a stream wait dumps its Python stack and exits instead of hanging the test
+    faulthandler.dump_traceback_later(int(os.environ.get("LD_WORKER_WATCHDOG_S", "600")), exit=True)
     transport, layouts = sys.argv[1], sys.argv[2:]
     world, rank = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"])
     one_gpu = os.environ.get("LD_WORKER_ONE_GPU", "0") == "1"

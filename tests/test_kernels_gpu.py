@@ -354,6 +354,33 @@ def test_row_kernels():
     report("sampler_update mode2 x", xo, den, 1e-5)
 
 
+def test_unpatchify_blocks_equals_unpatchify_epilogue():
+    """Token-major blocks scattered by `ld_unpatchify_blocks` (the copy-engine output exchange of the parallel layouts) ==
+    the UNPATCHIFY GEMM epilogue writing the latent layout directly, bit for bit; blocks in arbitrary order, two rows."""
+    torch.manual_seed(3)
+    T, Hp, Wp, D = 3, 5, 7, 128
+    n_img = T * Hp * Wp
+    a = (torch.randn(2 * n_img, D, device=dev) * 0.5).bfloat16()
+    w = (torch.randn(64, D, device=dev) * 0.05).bfloat16()
+    b = (torch.randn(64, device=dev) * 0.1).bfloat16()
+    want = torch.zeros(2, T, 16, 2 * Hp, 2 * Wp, device=dev, dtype=torch.bfloat16)
+    ops.gemm(a, w, epilogue=EPI_UNPATCHIFY, bias=b, out=want, rows_per_batch=n_img, tok_offset=0, text_len=0,
+             patch_grid=(T, Hp, Wp, 16))
+    tok = ops.gemm(a, w, epilogue=EPI_BIAS, bias=b).view(2, n_img, 64)
+    cuts = [0, 17, 60, n_img]
+    blocks = []
+    for r in (1, 0):
+        for i in (2, 0, 1):
+            g0, g1 = cuts[i], cuts[i + 1]
+            blocks.append((tok[r, g0:g1].contiguous(), r, g0, g1 - g0))
+    got = torch.full_like(want, float("nan"))
+    ops.unpatchify_blocks(blocks, got)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    with pytest.raises(ValueError):
+        ops.unpatchify_blocks([(tok[0], 0, n_img - 3, 10)], got)
+
+
 def test_attention_merge_equals_monolithic():
     """ring hop merge: attention over two K/V halves merged by (O, LSE) == attention over the whole K/V."""
     torch.manual_seed(3)

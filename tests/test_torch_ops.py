@@ -11,7 +11,7 @@ NS = torch.ops.landiff_b200
 
 
 def test_every_compute_entry_point_is_a_registered_op():
-    assert len(ops.TORCH_OPS) == 23
+    assert len(ops.TORCH_OPS) == 24
     for name in ops.TORCH_OPS:
         op = getattr(NS, name)
         assert "landiff_b200::" + name in str(op.default._schema)
