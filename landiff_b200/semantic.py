@@ -170,6 +170,15 @@ def pad_to_square(x: torch.Tensor, pad_values):
     return out
 
 
+def prepare_visual(visual: torch.Tensor, pad_values) -> torch.Tensor:
+    """[-1, 1] float frames [..., C, H, W] -> uint8 frames padded to a square, as the tokenizer expects them
+    (condition.py:118-123: (v + 1) / 2, clamp, torchvision `to_dtype(uint8, scale=True)` = multiply by 256 - 1e-3 and
+    truncate; condition.py:95-99: pad right / bottom with grey 127)."""
+    v = ((visual + 1.0) / 2.0).clamp(0, 1)
+    v = v.mul(255.0 + 1.0 - 1e-3).to(torch.uint8)
+    return pad_to_square(v, pad_values)
+
+
 class SemanticCond(nn.Module):
     """condition.py:30-137."""
 
@@ -220,13 +229,9 @@ class SemanticCond(nn.Module):
                 semantic_feature_before_upsample: torch.Tensor = None) -> torch.Tensor:
         target = None
         if visual is not None:
-            # [-1, 1] floats -> uint8 (condition.py:120-123; torchvision's to_dtype(scale=True) multiplies by 256 - 1e-3
-            # and truncates), then pad to a square with grey (condition.py:95-99)
-            visual = ((visual + 1.0) / 2.0).clamp(0, 1)
-            visual = visual.mul(255.0 + 1.0 - 1e-3).to(torch.uint8)
             oh, ow = visual.shape[-2:]
             target = (oh // self.dowsample_factor, ow // self.dowsample_factor)
-            visual = pad_to_square(visual, self.pad_values)
+            visual = prepare_visual(visual, self.pad_values)
         if semantic_feature_before_upsample is None:
             features = self.semantic_model(visual, indexs)
         else:

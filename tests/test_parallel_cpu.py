@@ -144,3 +144,27 @@ def test_ring_and_cfg_exchange_gloo_world2():
         assert err_sp == 0.0, f"rank {r}: SP-only output assembly wrong ({err_sp})"
         assert err < 1e-5 and err_l < 1e-5, f"rank {r}: ring attention differs from monolithic ({err}, {err_l})"
         assert err_c == 0.0, f"rank {r}: CFG assembly not exact"
+
+
+def test_output_gather_blocks_cover_every_token_once():
+    """Host logic of the copy-engine output exchange: for every layout the (row, g0, count) blocks of all ranks tile the
+    [2, n_img] output exactly once, and a rank's blocks sit at the right offsets of its buffer."""
+    from landiff_b200.parallel import Layout, OutputGather
+
+    text_len, n_img = 226, 17550
+    n_total = text_len + n_img
+    for world, cfg in [(2, 1), (4, 2), (8, 2), (4, 1), (16, 2)]:
+        sp = world // cfg
+        tok_rows = n_total // sp
+        cover = torch.zeros(2, n_img, dtype=torch.int32)
+        for rank in range(world):
+            og = OutputGather.__new__(OutputGather)
+            og.layout = Layout(world, 0, cfg, sp)
+            og.rows_local, og.tok_rows = (1 if cfg == 2 else 2), tok_rows
+            blocks = og.blocks_of(rank, 1 << 20, n_total, text_len)
+            assert len(blocks) == og.rows_local
+            for i, (addr, row, g0, count) in enumerate(blocks):
+                assert addr == (1 << 20) + i * tok_rows * 64 * 2 and 0 < count <= tok_rows
+                assert row == (rank // sp if cfg == 2 else i)
+                cover[row, g0:g0 + count] += 1
+        assert bool((cover == 1).all()), (world, cfg)

@@ -51,6 +51,25 @@ def test_drop_in_state_dict_contract():
         m(semantic_feature_before_upsample=torch.zeros(1, 1, S.SMALL.z_channels, 4, 4))
 
 
+def test_visual_preparation_matches_torchvision():
+    """The uint8 conversion and the grey square padding in front of the tokenizer == the torchvision calls the reference
+    makes (condition.py:15-27, 118-123)."""
+    tv = pytest.importorskip("torchvision.transforms.v2")
+    from landiff_b200.semantic import prepare_visual
+
+    g = torch.Generator().manual_seed(3)
+    for shape in [(1, 3, 3, 48, 80), (2, 2, 3, 64, 40), (1, 1, 3, 32, 32)]:
+        visual = torch.rand(shape, generator=g) * 2.4 - 1.2          # values beyond [-1, 1] exercise the clamp
+        want = ((visual + 1.0) / 2.0).clamp(0, 1)
+        want = tv.functional.to_dtype(want, dtype=torch.uint8, scale=True)
+        h, w = want.shape[-2:]
+        if h != w:
+            pad = (0, 0, h - w, 0) if h > w else (0, 0, 0, w - h)   # torchvision order: left, top, right, bottom
+            want = tv.functional.pad(want, list(pad), fill=[127, 127, 127])
+        got = prepare_visual(visual, [127, 127, 127])
+        assert got.dtype == torch.uint8 and torch.equal(got, want)
+
+
 def test_control_net_builds_the_drop_in_conditioner():
     """`modules.semantic_condition_config.target: landiff_b200.semantic.SemanticCond` inside the control network config."""
     from landiff_b200 import dit
