@@ -262,6 +262,12 @@ class CFGGroup:
     def my_row(self) -> int:
         return self.layout.cfg_rank if self.layout.cfg_size == 2 else -1
 
+    def close(self) -> None:
+        """Release the IPC buffers of the copy-engine output exchange (collective-free; call before the process group goes)."""
+        if self._gather is not None:
+            self._gather.close()
+            self._gather = None
+
     def assemble(self, net_local: torch.Tensor, row: int, owned_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """net_local: [1, T, C, H, W] (only this rank's token shard is meaningful when owned_mask is given)."""
         shape = (2,) + tuple(net_local.shape[1:])
