@@ -17,7 +17,6 @@ SAT-owned pieces (SelfAttention/MLP/LayerNorm/final_layernorm) follow SURVEY.md 
 from __future__ import annotations
 
 import importlib
-import math
 import sys
 from typing import Dict, List, Optional
 

@@ -13,7 +13,7 @@ copy-engine K|V exchange (landiff_b200/dma_ring.py), which a replay would repeat
 """
 from __future__ import annotations
 
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 

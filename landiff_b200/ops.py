@@ -6,7 +6,6 @@ The same functions are also registered as `torch.ops.landiff_b200.*` custom ops 
 from __future__ import annotations
 
 import ctypes as C
-import math
 from typing import Optional
 
 import torch

@@ -329,7 +329,6 @@ def attach(warp, layout: Layout, sp_group, device) -> None:
     """Configure a ControlDiffWarp for this rank: token shard + ring on both networks."""
     if layout.sp_size == 1:
         return
-    from .dit import SequenceShard
 
     for wrapper in (warp.control_model, warp.main_model):
         m = wrapper.diffusion_model
