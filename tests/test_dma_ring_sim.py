@@ -1,5 +1,5 @@
-"""CPU: discrete-event simulation of the copy-engine K|V exchange protocol (landiff_b200/dma_ring.py +
-RingAttention._attention_dma).
+"""CPU: discrete-event simulation of the copy-engine exchange protocols (landiff_b200/dma_ring.py): the per-layer K|V
+all-gather (RingAttention._attention_dma) and, at the end of the file, the per-step output exchange (OutputGather.gather).
 
 The REAL host code runs for every rank of a sequence-parallel group (PeerGather.push_all / kernel_shards / release_all
 and the per-layer schedule); only the three C-ABI calls it makes (stream wait-value, stream write-value, async copy),
@@ -284,3 +284,159 @@ def test_simulator_catches_a_missing_release_wait():
         sim2.run(random.Random(seed))
         bad += seen != [1, 2]
     assert bad > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The per-step OUTPUT exchange (parallel.OutputGather): the same PeerGather protocol over the whole world, consumed by a
+# plain kernel behind stream-level waits instead of in-kernel polls.
+
+def build_world(sim, world, cfg):
+    lib = FakeLib(sim)
+    sp = world // cfg
+    rows_local, tok_rows = (1 if cfg == 2 else 2), 2
+    shape = (rows_local, tok_rows, 64)
+    recv = [[torch.zeros(shape, dtype=torch.bfloat16) for _ in range(world - 1)] for _ in range(world)]
+    flag_base = [5000 * (r + 1) for r in range(world)]
+    out = []
+    for r in range(world):
+        for t in recv[r]:
+            sim.tensors[t.data_ptr()] = t
+        pg = object.__new__(dma_ring.PeerGather)
+        pg.lib, pg.device, pg.shape, pg.dtype = lib, "cpu", shape, torch.bfloat16
+        pg.nbytes = rows_local * tok_rows * 64 * 2
+        pg.n, pg.me = world, r
+        pg._flags_ptr = flag_base[r]
+        pg._peer_recv = {d: recv[(r + d) % world][d - 1].data_ptr() for d in range(1, world)}
+        pg._peer_flags = {d: flag_base[(r + d) % world] for d in range(1, world)}
+        pg.recv = recv[r]
+        pg.next_id, pg.last_sent = 1, 0
+        og = object.__new__(parallel.OutputGather)
+        og.layout = parallel.Layout(world, r, cfg, sp)
+        og.rows_local, og.tok_rows = rows_local, tok_rows
+        og.pg = pg
+        og.comm_stream = FakeStream(sim, f"ocomm{r}")
+        og._sent = None
+        og.compute_stream = FakeStream(sim, f"ocompute{r}")
+        local = torch.zeros(shape, dtype=torch.bfloat16)
+        sim.tensors[local.data_ptr()] = local
+        out.append((og, local))
+    return out
+
+
+def simulate_output_exchange(world, cfg, seed, monkeypatch, gather=None, mutate=None, n_steps=4):
+    from landiff_b200 import ops
+
+    sim = Sim()
+    FakeEvent.sim = sim
+    ranks = build_world(sim, world, cfg)
+    current = {}
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: current["og"].compute_stream)
+    monkeypatch.setattr(dma_ring, "check", lambda rc, what: None)
+
+    def owner_of(addr):
+        for base, t in sim.tensors.items():
+            if base <= addr < base + t.numel() * t.element_size():
+                return t
+        raise AssertionError(f"block address {addr} is not inside any simulated buffer")
+
+    def fake_unpatchify_blocks(blocks, out):
+        og, step = current["og"], current["step"]
+        r = og.layout.rank
+
+        def read(blocks=list(blocks), r=r, step=step):
+            for addr, row, g0, count in blocks:
+                t = owner_of(addr)
+                sim.log.append((r, step, row, g0, int(t.view(-1)[0]), int(t.view(-1)[1])))
+
+        sim.enqueue(og.compute_stream.cuda_stream, ("call", read))
+
+    monkeypatch.setattr(ops, "unpatchify_blocks", fake_unpatchify_blocks)
+    if mutate is not None:
+        for og, _ in ranks:
+            mutate(og)
+    order = [(s, r) for s in range(n_steps) for r in range(world)]
+    random.Random(seed).shuffle(order)
+    order.sort(key=lambda sr: sr[0])
+    n_total, text_len = 4 * (world // cfg) * 3, 2      # token counts only feed blocks_of's bookkeeping
+    for step, r in order:
+        og, local = ranks[r]
+        current.update(og=og, step=step)
+
+        def final_gemm(local=local, r=r, step=step):      # the final linear writes this rank's block: tag (rank, step)
+            local.view(-1)[0], local.view(-1)[1] = float(r), float(step)
+
+        sim.enqueue(og.compute_stream.cuda_stream, ("call", final_gemm))
+        (gather or parallel.OutputGather.gather)(og, local, None, n_total, text_len)
+    sim.run(random.Random(2000 + seed))
+    return sim.log
+
+
+def output_reads_are_correct(log, world, cfg, n_steps=4):
+    """Every rank, every step: one block per (row, shard) of the output, each carrying the tag of the rank that owns it and
+    of THIS step."""
+    sp = world // cfg
+    rows_local = 1 if cfg == 2 else 2
+    if len(log) != world * n_steps * world * rows_local:
+        return False
+    for r, step, row, g0, src_rank, src_step in log:
+        if src_step != step:
+            return False
+        if cfg == 2 and src_rank // sp != row:
+            return False
+    # every (row, shard) exactly once per (rank, step)
+    seen = {}
+    for r, step, row, g0, src_rank, _ in log:
+        seen.setdefault((r, step), []).append((row, src_rank % sp))
+    return all(sorted(v) == sorted((row, s) for row in range(2) for s in range(sp)) for v in seen.values())
+
+
+@pytest.mark.parametrize("world,cfg", [(2, 1), (4, 2), (8, 2), (4, 1)])
+def test_output_exchange_is_safe_and_live(world, cfg, monkeypatch):
+    for seed in range(8):
+        log = simulate_output_exchange(world, cfg, seed, monkeypatch)
+        assert output_reads_are_correct(log, world, cfg), f"world={world} cfg={cfg} seed={seed}"
+
+
+def _no_arrival_wait(og):
+    og.pg.wait_all = lambda T, stream: None
+
+
+def _no_release(og):
+    og.pg.release_all = lambda T, stream: None
+
+
+OUTPUT_SOURCE_MUTATIONS = {   # (old, new) on the dedented source of OutputGather.gather
+    "the next final GEMM may overwrite the block while it is being pushed": ("    compute.wait_event(self._sent)", "    pass"),
+    "the push does not wait for the final GEMM": ("    self.comm_stream.wait_event(ready)\n", ""),
+}
+OUTPUT_OBJECT_MUTATIONS = {
+    "the scatter kernel does not wait for the arrival flags": _no_arrival_wait,
+    "receive buffers are never released": _no_release,
+}
+
+
+@pytest.mark.parametrize("name", sorted(OUTPUT_SOURCE_MUTATIONS) + sorted(OUTPUT_OBJECT_MUTATIONS))
+def test_every_guard_of_the_output_exchange_is_necessary(name, monkeypatch):
+    import inspect
+    import textwrap
+
+    gather, mutate = None, None
+    if name in OUTPUT_SOURCE_MUTATIONS:
+        old, new = OUTPUT_SOURCE_MUTATIONS[name]
+        src = textwrap.dedent(inspect.getsource(parallel.OutputGather.gather))
+        assert old in src, "the mutation no longer matches the source; update OUTPUT_SOURCE_MUTATIONS"
+        ns = {}
+        exec(src.replace(old, new), dict(vars(parallel), torch=torch), ns)
+        gather = ns["gather"]
+    else:
+        mutate = OUTPUT_OBJECT_MUTATIONS[name]
+    broken = 0
+    for world, cfg in ((2, 1), (4, 2)):
+        for seed in range(16):
+            try:
+                broken += not output_reads_are_correct(
+                    simulate_output_exchange(world, cfg, seed, monkeypatch, gather=gather, mutate=mutate), world, cfg)
+            except AssertionError:      # deadlock
+                broken += 1
+    assert broken > 0, name
