@@ -162,7 +162,15 @@ int make_tmap_im2col3x3_bf16(CUtensorMap* out, const void* gptr, int C, int W, i
 extern "C" {
 
 const char* ld_last_error(void) { return ld::g_err; }
-int ld_abi_version(void) { return 6; }
+int ld_abi_version(void) { return 7; }
+
+/* sizes of the structs that cross the boundary, so that a binding can verify its mirror of them at load time */
+int ld_struct_sizes(int* gemm_args, int* kv_shard, int* token_blocks) {
+  if (gemm_args) *gemm_args = (int)sizeof(ld_gemm_args);
+  if (kv_shard) *kv_shard = (int)sizeof(ld_kv_shard);
+  if (token_blocks) *token_blocks = (int)sizeof(ld_token_blocks);
+  return LD_OK;
+}
 int ld_device_check(int* sms) {
   int rc = ld::check_device();
   if (rc == LD_OK && sms) *sms = ld::sm_count();

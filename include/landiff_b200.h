@@ -31,6 +31,8 @@ extern "C" {
 
 const char* ld_last_error(void);
 int ld_abi_version(void);
+/* sizeof(ld_gemm_args), sizeof(ld_kv_shard), sizeof(ld_token_blocks): a binding checks its mirrors against these at load */
+int ld_struct_sizes(int* gemm_args, int* kv_shard, int* token_blocks);
 /* 0 iff the current device is compute capability 10.x; fills sm_count if non-null. */
 int ld_device_check(int* sm_count);
 

@@ -57,6 +57,7 @@ _vp, _i, _f, _i64, _fp = C.c_void_p, C.c_int, C.c_float, C.c_int64, C.c_void_p
 SIGNATURES = {
     "ld_last_error": (C.c_char_p, []),
     "ld_abi_version": (C.c_int, []),
+    "ld_struct_sizes": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "ld_device_check": (C.c_int, [C.POINTER(C.c_int)]),
     "ld_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "ld_attention_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _fp, _fp, _i, _i, _i, _i, _i, _i, _i, _vp]),
@@ -96,7 +97,7 @@ def lib_path() -> Path:
     return _build.LIB_PATH
 
 
-ABI_VERSION = 6   # must equal ld_abi_version() of the loaded library (bumped whenever a signature or struct changes)
+ABI_VERSION = 7   # must equal ld_abi_version() of the loaded library (bumped whenever a signature or struct changes)
 
 
 def load() -> C.CDLL:
@@ -122,6 +123,13 @@ def load() -> C.CDLL:
     if got != ABI_VERSION:
         raise LanDiffB200Error(f"{path} reports ABI version {got}, the Python binding expects {ABI_VERSION}: "
                                "stale library — rebuild with `python -m landiff_b200.build --force`")
+    sz = [C.c_int(0) for _ in range(3)]
+    lib.ld_struct_sizes(*[C.byref(v) for v in sz])
+    for name, got_c, mirror in (("ld_gemm_args", sz[0].value, GemmArgs), ("ld_kv_shard", sz[1].value, KvShard),
+                                ("ld_token_blocks", sz[2].value, TokenBlocks)):
+        if got_c != C.sizeof(mirror):
+            raise LanDiffB200Error(f"{name}: the library's struct is {got_c} bytes, the Python mirror {C.sizeof(mirror)} — "
+                                   "include/landiff_b200.h and landiff_b200/_C.py have drifted apart")
     _lib = lib
     return lib
 
@@ -133,7 +141,7 @@ class LanDiffB200Error(RuntimeError):
 LAUNCHES = [0]  # KERNELS launched through the C-ABI (every compute entry point launches exactly one kernel)
 # entry points that launch no kernel: queries, allocation, copy-engine copies and stream memory operations
 _NO_KERNEL = {"ld_device_check", "ld_ipc_alloc", "ld_ipc_open", "ld_ipc_close", "ld_ipc_free", "ld_copy_async",
-              "ld_stream_write_u32", "ld_stream_wait_geq_u32", "ld_attention_status", "ld_attention_workspace_bytes", "w"}
+              "ld_stream_write_u32", "ld_stream_wait_geq_u32", "ld_attention_status", "ld_attention_workspace_bytes", "ld_struct_sizes", "w"}
 
 
 def check(rc: int, what: str) -> None:
