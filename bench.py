@@ -320,6 +320,10 @@ def run_ours(args):
                                            dit.InferValueRegistry.get_value("semantic_feature"))
                 eager["ours_over_eager"] = round(value / eager["value"], 4)
                 line["gpu_eager_baseline"] = eager
+                try:
+                    line["semantic_conditioner"] = semantic_conditioner_leg(dev)
+                except Exception as exc:  # noqa: BLE001  (informational leg: never fail the bench line)
+                    line["semantic_conditioner"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -434,6 +438,68 @@ def gpu_eager_baseline(warp, cfg, x_dev, ctx2, sem, steps=3):
             "what": "reference module graph (oracle restatement), PyTorch eager bf16 on this GPU: cuBLAS + SDPA, same shape, "
                     "CFG batch 2, network evaluation only (the eager sampler update adds < 0.2 ms)",
             "clocks": clk}
+
+
+# ---------------------------------------------------------------------------------------------------- row f2
+def semantic_conditioner_leg(dev, frames=13, h=30, w=45, iters=5):
+    """Once-per-video cost of the semantic conditioner's conv decoder (landiff_b200/semantic.py)
+    at the shipped widths on the 480x720 feature grid, next to the same graph in PyTorch eager bf16 (cuDNN).  Informational
+    (N = 1, outside the timed region): the headline metric is the 50-step denoise."""
+    import torch.nn.functional as F
+
+    from landiff_b200.semantic import SemanticCond
+
+    dec = dict(z_channels=768, resolution=16, in_channels=512, out_ch=64, ch=512, ch_mult=[0.25, 1], num_res_blocks=4,
+               attn_resolutions=[], dropout=0.0, use_mid_attention=False, upsample_type="pixelshuffle")
+    torch.manual_seed(7)
+    m = SemanticCond(semantic_model_config={"target": "torch.nn.Identity"}, upsample_model_config={"target": "-", "params": dec},
+                     dtype=torch.bfloat16, out_dim=64, target_dim=16, zero_init_conv_out=False).to(dev)
+    feat = torch.randn(1, frames, 768, h, w, device=dev).bfloat16()
+    sd = {k: v for k, v in m.state_dict().items()}
+
+    def eager():     # vq_gan_blocks.py:577-606 + condition.py:131-136 with torch ops on the same parameters
+        gn = lambda x, n: F.group_norm(x, 32, sd[n + ".weight"], sd[n + ".bias"], eps=1e-6)
+        conv = lambda x, n, p=1: F.conv2d(x, sd[n + ".weight"], sd[n + ".bias"], padding=p)
+        sw = lambda x: x * torch.sigmoid(x)
+
+        def res(x, n):
+            hh = conv(sw(gn(x, n + ".norm1")), n + ".conv1")
+            hh = conv(sw(gn(hh, n + ".norm2")), n + ".conv2")
+            return (conv(x, n + ".nin_shortcut", 0) if n + ".nin_shortcut.weight" in sd else x) + hh
+
+        u = "upsample_model."
+        x = conv(feat[0], u + "conv_in")
+        x = res(res(x, u + "mid.block_1"), u + "mid.block_2")
+        for j in range(5):
+            x = res(x, f"{u}up.1.block.{j}")
+        x = conv(F.pixel_shuffle(x, 2), u + "up.1.upsample.conv")
+        for j in range(5):
+            x = res(x, f"{u}up.0.block.{j}")
+        return conv(conv(sw(gn(x, u + "norm_out")), u + "conv_out"), "conv_out")
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            y = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters, y
+
+    ours_ms, y = timed(lambda: m(semantic_feature_before_upsample=feat))
+    eager_ms, y_ref = timed(eager)
+    rel = ((y[0].float() - y_ref.float()).norm() / y_ref.float().norm()).item()
+    del m, sd, y, y_ref
+    torch.cuda.empty_cache()
+    return {"ms_per_video": round(ours_ms, 3), "eager_bf16_ms_per_video": round(eager_ms, 3),
+            "ours_over_eager": round(ours_ms / eager_ms, 3),
+            "rel_l2_between_the_two_bf16_runs": round(rel, 5),   # each is ~1e-2 from fp32 (tests/test_semantic.py has the fp32 gates)
+            "what": f"SemanticCond upsample path, {frames} frames of 768 x {h} x {w} features -> 16 x {2 * h} x {2 * w}: implicit-GEMM "
+                    "convolutions (TMA im2col gather) + GroupNorm kernels; beside it the same graph with torch ops (cuDNN) on the "
+                    "same bf16 parameters"}
 
 
 # ---------------------------------------------------------------------------------------------------- CPU side
