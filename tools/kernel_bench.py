@@ -133,28 +133,15 @@ def main():
         print(f"  sampler_update: {ms:8.4f} ms  {gb / ms * 1e3:7.1f} GB/s", flush=True)
     if "semantic" in a.cases:
         # the semantic conditioner's upsample path, once per video: 13 frames of 768 x 30 x 45 features
-        # -> [1, 13, 16, 60, 90]; beside it the same graph in PyTorch eager bf16 (cuDNN convolutions, channels-first)
-        sys.path.insert(0, str(ROOT))
-        from oracle import semantic_oracle as S   # tools/ may use the oracle for weights / shapes (bench side only)
-        from landiff_b200.semantic import SemanticCond
-        cfg = S.SHIPPED
-        sd = {k: v.bfloat16() for k, v in S.random_state_dict(cfg, 31).items()}
-        m = SemanticCond(**cfg.cond_kwargs("landiff.diffusion.semantic_models.modules.vq_gan_blocks.Decoder", torch.bfloat16))
-        m.load_state_dict(sd, strict=True)
-        m = m.cuda()
-        feat = S.features_for(cfg, 32, 1, 13, 30, 45).cuda().bfloat16()
-        ms = timeit(lambda: m(semantic_feature_before_upsample=feat), a.iters)
-        flops = 0.0
-        for name, shp in S.param_shapes(cfg).items():
-            if len(shp) == 4:
-                hi = (".up.0." in name) or ("up.1.upsample" in name) or name.endswith("upsample_model.conv_out.weight") or name == "conv_out.weight"
-                flops += 2.0 * shp[0] * shp[1] * shp[2] * shp[3] * 13 * (60 * 90 if hi else 30 * 45)
-        print(f"  semantic conditioner (13 frames, 30x45 -> 60x90): {ms:8.3f} ms  {flops / ms / 1e9:7.1f} TFLOP/s of convolution "
-              f"({flops / 1e12:.2f} TFLOP)", flush=True)
-        sdg = {k: v.cuda() for k, v in sd.items()}
-        ms_e = timeit(lambda: S.semantic_oracle(sdg, feat, cfg), a.iters)
-        print(f"  [same graph, torch eager bf16 (cuDNN): {ms_e:8.3f} ms; ours / eager = {ms / ms_e:.2f}]", flush=True)
+        # -> [1, 13, 16, 60, 90]; beside it the same graph with torch ops (cuDNN) — the leg bench.py reports
+        import bench
 
+        r = bench.semantic_conditioner_leg(torch.device(dev), iters=a.iters)
+        flops = 1.66e12   # convolution FLOPs of the shipped decoder on 13 frames
+        print(f"  semantic conditioner (13 frames, 30x45 -> 60x90): {r['ms_per_video']:8.3f} ms  "
+              f"{flops / r['ms_per_video'] / 1e9:7.1f} TFLOP/s of convolution (1.66 TFLOP)", flush=True)
+        print(f"  [same graph, torch eager bf16 (cuDNN): {r['eager_bf16_ms_per_video']:8.3f} ms; ours / eager = {r['ours_over_eager']:.2f}]",
+              flush=True)
 
 if __name__ == "__main__":
     main()
