@@ -1140,8 +1140,9 @@ extern "C" int ld_attention_shards_ws_bf16(const void* q, const ld_kv_shard* sha
   //         1: exact path only (per-block maxima, lazy rescaling)
   //         2 / 3 / 4: fast path with 0 / 5 / 6 of 16 pairs on the polynomial   5: variant 0 with truncating bf16 pack
   //         6: variant 0 with one CTA per query block even in the last wave (no tail split)
-  // share of exponential pairs on the FMA-pipe polynomial for the default variants (0, 6): LD_ATTN_KP = 2..6 (A/B switch)
-  static const int kp_default = [] { const char* e = getenv("LD_ATTN_KP"); const int v = e ? atoi(e) : 0; return (v >= 2 && v <= 6) ? v : kDefaultKP; }();
+  // share of exponential pairs on the FMA-pipe polynomial for the default variants (0, 6): LD_ATTN_KP = 4 | 5 | 6 (A/B switch
+  // between the shipped default, the boost-clock optimum and one step beyond; the sweep over 2..6 is in profiles/)
+  static const int kp_default = [] { const char* e = getenv("LD_ATTN_KP"); const int v = e ? atoi(e) : 0; return (v >= 4 && v <= 6) ? v : kDefaultKP; }();
   switch (variant) {
     case 0:
     case 6:   // 6: variant 0 with one CTA per query block even in the last wave (no tail split)
@@ -1150,8 +1151,6 @@ extern "C" int ld_attention_shards_ws_bf16(const void* q, const ld_kv_shard* sha
         return launch_attn5<kDefaultKP, false, true>(sh, prm, grid, st);
       }
       switch (kp_default) {
-        case 2: return launch_attn5<2, false>(sh, prm, grid, st);
-        case 3: return launch_attn5<3, false>(sh, prm, grid, st);
         case 6: return launch_attn5<6, false>(sh, prm, grid, st);
         case 5: return launch_attn5<5, false>(sh, prm, grid, st);
         default: return launch_attn5<4, false>(sh, prm, grid, st);
